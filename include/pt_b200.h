@@ -1,0 +1,168 @@
+/* pt_b200.h — C ABI of the B200-native trace path (libpt_b200.so).
+ *
+ * Drop-in seam: the public interface of the reference's `class Pathtracer`
+ * (reference: PathtracerCUDA/src/pathtracer/Pathtracer.h:12-69).  Each entry point below cites the reference
+ * method it replaces.  Plain pointers and sizes only; no C++/torch types.  All calls are blocking, like the
+ * reference (Pathtracer.cpp:199 cudaDeviceSynchronize after every launch).
+ *
+ * Conventions
+ *   - every int-returning call returns PT_OK (0) or a negative PT_E_* code; pt_last_error() gives the text
+ *     (the reference prints "CUDA error = ..." and exit()s, Pathtracer.cpp:17-28; the CLI reproduces that).
+ *   - images are bottom-row-first (pixel y=0 is the bottom of the view), RGBA, exactly as the reference's
+ *     accumulation buffer (kernels/trace.cu:181,196-198).
+ *   - there is NO CPU fallback: without a CUDA device pt_create fails with PT_E_NO_DEVICE.
+ */
+#ifndef PT_B200_H
+#define PT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PT_OK 0
+#define PT_E_INVALID (-1)
+#define PT_E_NO_DEVICE (-2)
+#define PT_E_CUDA (-3)
+#define PT_E_IO (-4)
+#define PT_E_PARSE (-5)
+#define PT_E_LIMIT (-6)
+
+/* reference: enum class HittableType, Hittable.h:9-12 (same numeric values) */
+enum { PT_SPHERE = 0, PT_CYLINDER = 1, PT_DISK = 2, PT_CONE = 3, PT_PARABOLOID = 4, PT_QUAD = 5, PT_CUBE = 6 };
+/* reference: enum class MaterialType, Material.h:9-12 */
+enum { PT_LAMBERT = 0, PT_GGX = 1, PT_LAMBERT_GGX = 2 };
+
+/* arguments of the reference Material ctor (Material.h:17): type, baseColor, emissive, roughness, metalness,
+ * textureIndex (1-based texture handle, 0 = none). */
+typedef struct pt_material_desc {
+	uint32_t type;
+	float base_color[3];
+	float emissive[3];
+	float roughness;
+	float metalness;
+	uint32_t texture;
+} pt_material_desc;
+
+/* arguments of the reference CpuHittable ctor (Hittable.h:45): type, position, rotation (Euler XYZ, RADIANS),
+ * scale, material. */
+typedef struct pt_object_desc {
+	uint32_t type;
+	float position[3];
+	float rotation[3];
+	float scale[3];
+	pt_material_desc material;
+} pt_object_desc;
+
+/* arguments of the reference Camera ctor (Camera.h:7): position, lookat, up, fovy (RADIANS), aspectRatio. */
+typedef struct pt_camera_desc {
+	float position[3];
+	float look_at[3];
+	float up[3];
+	float fovy;
+	float aspect;
+} pt_camera_desc;
+
+/* counters of the last pt_render call (the wavefront queues make these free; SURVEY.md §5 "Tracing"). */
+typedef struct pt_stats {
+	uint64_t samples;      /* paths started (= W*H*spp) */
+	uint64_t rays;         /* closest-hit queries (camera + scattered segments, <=5 per sample) */
+	uint64_t node_visits;  /* BVH node box-pair tests (only counted when option "count_work" = 1) */
+	uint64_t prim_tests;   /* primitive intersection tests (idem) */
+	uint64_t shades;       /* Material::sample evaluations (idem) */
+	uint64_t misses;       /* environment lookups (idem) */
+	float gpu_ms;          /* CUDA-event time of the trace stage, same as pt_get_timing_ms */
+	uint32_t bvh_nodes;
+	uint32_t bvh_depth;
+	uint32_t scene_bytes;  /* device bytes of nodes + primitives + materials */
+	uint32_t scene_in_smem;/* 1 if the scene was staged into shared memory by TMA bulk copy */
+} pt_stats;
+
+typedef struct pt_context pt_context;
+
+/* Pathtracer::Pathtracer(width, height, openglPixelBuffer = 0)   Pathtracer.h:15, Pathtracer.cpp:30-68.
+ * `device` is the CUDA ordinal (the reference hard-wires 0, Pathtracer.cpp:40).  No GL interop. */
+int pt_create(uint32_t width, uint32_t height, int device, pt_context **out);
+/* Pathtracer::~Pathtracer   Pathtracer.cpp:70-109 */
+void pt_destroy(pt_context *ctx);
+
+/* Pathtracer::setScene(count, hittables)   Pathtracer.h:22, Pathtracer.cpp:111-160.  Copies the input, builds the
+ * BVH, replaces the previous scene.  count == 0 prints the reference's message and is a no-op returning PT_OK. */
+int pt_set_scene(pt_context *ctx, size_t count, const pt_object_desc *objects);
+
+/* Pathtracer::loadTexture(path)   Pathtracer.h:35, Pathtracer.cpp:234-292.  Returns a 1-based handle, 0 on failure or
+ * when 64 textures exist.  ".hdr" (Radiance RGBE) -> float RGBA, anything else (PNG) -> 8-bit RGBA. */
+uint32_t pt_load_texture(pt_context *ctx, const char *path);
+/* same, from decoded RGBA texels already in host memory (is_hdr: float[4] per texel, else uint8[4]). */
+uint32_t pt_load_texture_mem(pt_context *ctx, uint32_t width, uint32_t height, int is_hdr, const void *rgba);
+
+/* Pathtracer::setSkyboxTextureHandle(handle)   Pathtracer.h:38, Pathtracer.cpp:294-297.  0 = black environment. */
+int pt_set_skybox(pt_context *ctx, uint32_t handle);
+
+/* Pathtracer::render(camera, spp, ignoreHistory)   Pathtracer.h:26, Pathtracer.cpp:162-227.  Synchronous.  Adds `spp`
+ * samples per pixel to the accumulation (or restarts it).  spp == 0 or no scene -> no kernel. */
+int pt_render(pt_context *ctx, const pt_camera_desc *camera, uint32_t spp, int ignore_history);
+
+/* Pathtracer::getTiming()   Pathtracer.h:29, Pathtracer.cpp:229-232.  GPU ms of the last pt_render. */
+float pt_get_timing_ms(const pt_context *ctx);
+
+/* Pathtracer::getHDRImageData()   Pathtracer.h:41, Pathtracer.cpp:299-315.  Library-owned W*H*4 floats, valid until
+ * the next call on ctx.  Normalised exactly like the reference: accumulation / number of render() calls
+ * (SURVEY.md Q1), all four channels scaled. */
+const float *pt_get_hdr(pt_context *ctx);
+/* Pathtracer::getImageData()   Pathtracer.h:44, Pathtracer.cpp:317-339 + kernels/tonemap.cu:4-27.  Library-owned
+ * W*H*4 bytes RGBA8 (A = 255): mean -> Reinhard -> gamma 1/2.2 -> truncate. */
+const uint8_t *pt_get_ldr(pt_context *ctx);
+
+/* ---- extensions (not in the reference class; used by the CLI, the tests and the bench) ---- */
+
+/* W*H*4 floats of the TRUE per-sample mean (accumulation / total samples), library-owned. */
+const float *pt_get_hdr_mean(pt_context *ctx);
+
+/* Options (all doubles):
+ *  "seed"            Philox key (default 1984, cf. kernels/initRandState.cu:16)
+ *  "sample_offset"   global index of the first sample of the next pt_render (multi-GPU sample partition)
+ *  "sample_stride"   distance between this context's consecutive global sample indices (1 = contiguous)
+ *  "frames_per_spp"  k>0: a pt_render of spp samples counts ceil(spp/k) frames for the Q1 normalisation
+ *                    (k=8 reproduces the reference headless CLI, main.cpp:271-278); 0: one frame per call
+ *  "count_work"      1: count node visits / primitive tests / shades / misses (slower)
+ *  "smem_scene"      0: never stage the scene in shared memory; 1: auto (default)
+ *  "max_bounces"     path segments, default 5 (kernels/trace.cu:109) */
+int pt_set_option(pt_context *ctx, const char *key, double value);
+int pt_get_stats(const pt_context *ctx, pt_stats *out);
+
+/* Deterministic primary-ray pass (parity gate): pixel-centre rays u=(x+0.5)/W, v=(y+0.5)/H, t_min=0.001; writes the
+ * scene-order object index (or -1) and hit t (0 on miss) per pixel into HOST buffers of W*H elements. */
+int pt_primary_pass(pt_context *ctx, const pt_camera_desc *camera, int32_t *hit_index, float *hit_t);
+
+/* Closest-hit queries for caller-supplied rays (n rays, origin/direction as xyz triples in host memory). */
+int pt_trace_rays(pt_context *ctx, size_t n, const float *origins, const float *directions, float t_min,
+                  int32_t *hit_index, float *hit_t, float *hit_normal);
+
+/* Device pointer of the float4 accumulation buffer (W*H*4 floats) for the multi-GPU reduce, and a setter so the
+ * caller can supply its own allocation (e.g. a torch tensor reduced with torch.distributed / NCCL). */
+void *pt_accum_device_ptr(pt_context *ctx);
+int pt_set_accum_device_ptr(pt_context *ctx, void *device_ptr);
+
+/* loadScene(pathtracer, params)   SceneLoader.cpp:124-348: parse the JSON scene, load its textures (paths relative to
+ * the process CWD), set scene + skybox, return the camera for aspect = width/height of ctx. */
+int pt_load_scene_file(pt_context *ctx, const char *json_path, pt_camera_desc *camera_out);
+/* parse only: fills up to `capacity` objects, returns the object count (or a negative error).  Texture paths are
+ * returned as indices into a '\n'-joined list written to tex_paths (may be NULL). */
+int pt_parse_scene_file(const char *json_path, pt_object_desc *objects, size_t capacity, pt_camera_desc *camera_out,
+                        float aspect, char *tex_paths, size_t tex_paths_cap, int32_t *skybox_tex_index);
+
+/* stbi_write_png / stbi_write_hdr with flip-on-write   main.cpp:180-199.  data is bottom-row-first RGBA. */
+int pt_write_png(const char *path, uint32_t width, uint32_t height, const uint8_t *rgba);
+int pt_write_hdr(const char *path, uint32_t width, uint32_t height, const float *rgba);
+/* decoders used by pt_load_texture (stbi_load / stbi_loadf replacement).  Caller frees with pt_free. */
+int pt_read_image(const char *path, uint32_t *width, uint32_t *height, int *is_hdr, void **rgba);
+void pt_free(void *p);
+
+const char *pt_last_error(void);
+const char *pt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
