@@ -265,3 +265,32 @@ class RefHost:
         accum = np.zeros((h, w, 4), np.float32)
         rays = self.L.refh_render(w, h, spp, seed_base, _p(accum))
         return accum, rays
+
+
+def write_blob(path, objects, cam, width, height):
+    """scene blob for oracle/_ref/ref_gpu (see oracle/ref_harness/ref_gpu.cu)"""
+    import struct
+    arr = object_array(objects)
+    with open(path, "wb") as f:
+        f.write(struct.pack("<4I", 0x32425450, width, height, len(objects)))
+        f.write(bytes(cam))
+        f.write(bytes(arr)[: len(objects) * C.sizeof(ObjectDesc)])
+
+
+def ref_gpu_primary(objects, cam, width, height, workdir):
+    """run the reference's own hitBVH on the GPU for pixel-centre rays -> (scene-order index, t)"""
+    blob = os.path.join(workdir, "scene.blob")
+    out = os.path.join(workdir, "primary.bin")
+    write_blob(blob, objects, cam, width, height)
+    subprocess.check_call([REF_GPU, "primary", blob, out], stdout=subprocess.DEVNULL)
+    n = width * height
+    raw = np.fromfile(out, np.uint8)
+    return raw[: n * 4].view(np.int32).copy(), raw[n * 4: n * 8].view(np.float32).copy()
+
+
+def ref_gpu_count(objects, cam, width, height, spp, workdir):
+    """rays the reference traceKernel traces for this scene/size/spp (its own seeds and 8-spp slicing)"""
+    import json
+    blob = os.path.join(workdir, "scene.blob")
+    write_blob(blob, objects, cam, width, height)
+    return json.loads(subprocess.check_output([REF_GPU, "count", blob, str(spp)]).decode().strip().splitlines()[-1])

@@ -466,7 +466,7 @@ void orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
 	out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 /* same map as cuRAND's curand_uniform (curand_kernel.h _curand_uniform): (0, 1] */
-float orc_uniform(uint32_t x) { return x * 2.3283064365386963e-10f + (2.3283064365386963e-10f / 2.0f); }
+float orc_uniform(uint32_t x) { return fmaf((float)x, 2.3283064365386963e-10f, 1.16415321826934814453125e-10f); }
 
 /* ---- textures: tex2D<float4> linear / normalized / wrap-U clamp-V (Pathtracer.cpp:276-281) in fp32 --------- */
 static void texLookup(const tex_t *t, float u, float v, float out[4])

@@ -1,0 +1,188 @@
+#include "json_min.h"
+#include <cstdlib>
+#include <cstring>
+
+namespace ptb
+{
+namespace
+{
+struct Parser
+{
+	const char *s;
+	size_t n, i = 0;
+	std::string err;
+	int depth = 0;
+
+	bool fail(const char *m)
+	{
+		if (err.empty()) err = std::string("JSON parse error at byte ") + std::to_string(i) + ": " + m;
+		return false;
+	}
+	void ws() { while (i < n && (s[i] == ' ' || s[i] == '\t' || s[i] == '\n' || s[i] == '\r')) ++i; }
+
+	static void appendUtf8(std::string &o, unsigned cp)
+	{
+		if (cp < 0x80) o += char(cp);
+		else if (cp < 0x800) { o += char(0xC0 | (cp >> 6)); o += char(0x80 | (cp & 0x3F)); }
+		else if (cp < 0x10000) { o += char(0xE0 | (cp >> 12)); o += char(0x80 | ((cp >> 6) & 0x3F)); o += char(0x80 | (cp & 0x3F)); }
+		else { o += char(0xF0 | (cp >> 18)); o += char(0x80 | ((cp >> 12) & 0x3F)); o += char(0x80 | ((cp >> 6) & 0x3F)); o += char(0x80 | (cp & 0x3F)); }
+	}
+	bool hex4(unsigned &v)
+	{
+		if (i + 4 > n) return fail("truncated \\u escape");
+		v = 0;
+		for (int k = 0; k < 4; ++k)
+		{
+			char c = s[i++];
+			v <<= 4;
+			if (c >= '0' && c <= '9') v |= unsigned(c - '0');
+			else if (c >= 'a' && c <= 'f') v |= unsigned(c - 'a' + 10);
+			else if (c >= 'A' && c <= 'F') v |= unsigned(c - 'A' + 10);
+			else return fail("bad \\u escape");
+		}
+		return true;
+	}
+	bool string(std::string &o)
+	{
+		++i; // opening quote
+		while (true)
+		{
+			if (i >= n) return fail("unterminated string");
+			unsigned char c = (unsigned char)s[i++];
+			if (c == '"') return true;
+			if (c < 0x20) return fail("control character in string");
+			if (c != '\\') { o += char(c); continue; }
+			if (i >= n) return fail("unterminated escape");
+			char e = s[i++];
+			switch (e)
+			{
+			case '"': o += '"'; break;
+			case '\\': o += '\\'; break;
+			case '/': o += '/'; break;
+			case 'b': o += '\b'; break;
+			case 'f': o += '\f'; break;
+			case 'n': o += '\n'; break;
+			case 'r': o += '\r'; break;
+			case 't': o += '\t'; break;
+			case 'u':
+			{
+				unsigned cp = 0;
+				if (!hex4(cp)) return false;
+				if (cp >= 0xD800 && cp <= 0xDBFF && i + 1 < n && s[i] == '\\' && s[i + 1] == 'u')
+				{
+					i += 2;
+					unsigned lo = 0;
+					if (!hex4(lo)) return false;
+					if (lo >= 0xDC00 && lo <= 0xDFFF) cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+					else return fail("bad surrogate pair");
+				}
+				appendUtf8(o, cp);
+				break;
+			}
+			default: return fail("bad escape");
+			}
+		}
+	}
+	bool number(JsonValue &v)
+	{
+		size_t b = i;
+		bool isFloat = false;
+		if (i < n && s[i] == '-') ++i;
+		if (i >= n || s[i] < '0' || s[i] > '9') return fail("bad number");
+		if (s[i] == '0') ++i;
+		else while (i < n && s[i] >= '0' && s[i] <= '9') ++i;
+		if (i < n && s[i] == '.')
+		{
+			isFloat = true;
+			++i;
+			if (i >= n || s[i] < '0' || s[i] > '9') return fail("bad fraction");
+			while (i < n && s[i] >= '0' && s[i] <= '9') ++i;
+		}
+		if (i < n && (s[i] == 'e' || s[i] == 'E'))
+		{
+			isFloat = true;
+			++i;
+			if (i < n && (s[i] == '+' || s[i] == '-')) ++i;
+			if (i >= n || s[i] < '0' || s[i] > '9') return fail("bad exponent");
+			while (i < n && s[i] >= '0' && s[i] <= '9') ++i;
+		}
+		std::string tok(s + b, i - b);
+		v.kind = isFloat ? JsonValue::Float : JsonValue::Int;
+		v.num = strtod(tok.c_str(), nullptr);
+		return true;
+	}
+	bool value(JsonValue &v)
+	{
+		ws();
+		if (i >= n) return fail("unexpected end of input");
+		if (++depth > 256) return fail("nesting too deep");
+		bool ok = true;
+		char c = s[i];
+		if (c == '{')
+		{
+			v.kind = JsonValue::Object;
+			++i;
+			ws();
+			if (i < n && s[i] == '}') { ++i; }
+			else
+				while (true)
+				{
+					ws();
+					if (i >= n || s[i] != '"') { ok = fail("expected object key"); break; }
+					std::string key;
+					if (!string(key)) { ok = false; break; }
+					ws();
+					if (i >= n || s[i] != ':') { ok = fail("expected ':'"); break; }
+					++i;
+					JsonValue child;
+					if (!value(child)) { ok = false; break; }
+					v.obj[key] = std::move(child);
+					ws();
+					if (i < n && s[i] == ',') { ++i; continue; }
+					if (i < n && s[i] == '}') { ++i; break; }
+					ok = fail("expected ',' or '}'");
+					break;
+				}
+		}
+		else if (c == '[')
+		{
+			v.kind = JsonValue::Array;
+			++i;
+			ws();
+			if (i < n && s[i] == ']') { ++i; }
+			else
+				while (true)
+				{
+					JsonValue child;
+					if (!value(child)) { ok = false; break; }
+					v.arr.push_back(std::move(child));
+					ws();
+					if (i < n && s[i] == ',') { ++i; continue; }
+					if (i < n && s[i] == ']') { ++i; break; }
+					ok = fail("expected ',' or ']'");
+					break;
+				}
+		}
+		else if (c == '"') { v.kind = JsonValue::String; ok = string(v.str); }
+		else if (c == '-' || (c >= '0' && c <= '9')) ok = number(v);
+		else if (n - i >= 4 && !strncmp(s + i, "true", 4)) { v.kind = JsonValue::Bool; v.b = true; i += 4; }
+		else if (n - i >= 5 && !strncmp(s + i, "false", 5)) { v.kind = JsonValue::Bool; v.b = false; i += 5; }
+		else if (n - i >= 4 && !strncmp(s + i, "null", 4)) { v.kind = JsonValue::Null; i += 4; }
+		else ok = fail("unexpected character");
+		--depth;
+		return ok;
+	}
+};
+} // namespace
+
+bool parseJson(const std::string &text, JsonValue &out, std::string &err)
+{
+	Parser p{ text.data(), text.size() };
+	// nlohmann skips a UTF-8 byte-order mark
+	if (p.n >= 3 && (unsigned char)p.s[0] == 0xEF && (unsigned char)p.s[1] == 0xBB && (unsigned char)p.s[2] == 0xBF) p.i = 3;
+	if (!p.value(out)) { err = p.err; return false; }
+	p.ws();
+	if (p.i != p.n) { p.fail("trailing characters"); err = p.err; return false; }
+	return true;
+}
+} // namespace ptb

@@ -1,0 +1,510 @@
+// pt_capi.cu — the C ABI of include/pt_b200.h: a resource-owning context that mirrors the reference's `class Pathtracer`
+// (Pathtracer.h:12-69, Pathtracer.cpp:30-339) method for method.  Blocking calls, one CUDA stream per context,
+// no CPU fallback (pt_create fails without a device).
+#include "../../include/pt_b200.h"
+#include "image_io.h"
+#include "scene_compile.h"
+#include "scene_loader.h"
+#include "trace_kernels.h"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace ptb;
+
+namespace
+{
+thread_local std::string g_lastError;
+int setError(int code, const std::string &msg)
+{
+	g_lastError = msg;
+	return code;
+}
+constexpr uint32_t kMaxTextures = 64; // MAX_TEXTURE_COUNT, Pathtracer.cpp:15
+} // namespace
+
+struct pt_context
+{
+	int device = 0;
+	uint32_t width = 0, height = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t evStart = nullptr, evStop = nullptr;
+	float4 *accum = nullptr;
+	bool ownAccum = true;
+	float4 *scaledDev = nullptr;
+	uchar4 *ldrDev = nullptr;
+	float *hostHdr = nullptr;     // pinned
+	uint8_t *hostLdr = nullptr;   // pinned
+	unsigned long long *counters = nullptr;
+	// scene
+	float4 *sceneBlob = nullptr;
+	Mat *mats = nullptr;
+	uint32_t nodeCount = 0, primCount = 0, bvhDepth = 0;
+	// textures
+	std::vector<void *> texMem;
+	TexDesc texHost[kMaxTextures];
+	TexDesc *texDev = nullptr;
+	uint32_t textureCount = 0, skybox = 0;
+	// state mirrored from the reference
+	float timingMs = 0.0f;
+	uint32_t accumulatedFrames = 0;
+	unsigned long long totalSamples = 0;
+	// options
+	uint64_t seed = 1984;
+	uint32_t sampleOffset = 0, sampleStride = 1, sampleCursor = 0;
+	uint32_t framesPerSpp = 0, maxBounces = 5, maxLeaf = 4;
+	LaunchConfig launch;
+	pt_stats stats;
+};
+
+#define CK(expr)                                                                                                      \
+	do                                                                                                                \
+	{                                                                                                                 \
+		cudaError_t e_ = (expr);                                                                                      \
+		if (e_ != cudaSuccess)                                                                                        \
+		{                                                                                                             \
+			char buf[512];                                                                                            \
+			snprintf(buf, sizeof buf, "CUDA error = %u at %s:%d '%s' (%s)", (unsigned)e_, __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+			return setError(PT_E_CUDA, buf);                                                                          \
+		}                                                                                                             \
+	} while (0)
+
+extern "C"
+{
+
+const char *pt_last_error(void) { return g_lastError.c_str(); }
+const char *pt_version(void) { return "pathtracercuda_b200 0.1 (sm_100a)"; }
+void pt_free(void *p) { free(p); }
+
+int pt_create(uint32_t width, uint32_t height, int device, pt_context **out)
+{
+	if (!out || width == 0 || height == 0) return setError(PT_E_INVALID, "pt_create: bad arguments");
+	*out = nullptr;
+	int count = 0;
+	if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+	{
+		cudaGetLastError();
+		return setError(PT_E_NO_DEVICE, "pt_create: no CUDA device (this library has no CPU fallback)");
+	}
+	if (device < 0 || device >= count) return setError(PT_E_INVALID, "pt_create: device ordinal out of range");
+	pt_context *c = new pt_context();
+	c->device = device;
+	c->width = width;
+	c->height = height;
+	memset(&c->stats, 0, sizeof c->stats);
+	memset(c->texHost, 0, sizeof c->texHost);
+	const size_t px = size_t(width) * height;
+#define CKC(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { char buf[512]; snprintf(buf, sizeof buf, "CUDA error = %u at %s:%d '%s' (%s)", (unsigned)e_, __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); g_lastError = buf; pt_destroy(c); return PT_E_CUDA; } } while (0)
+	CKC(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CKC(cudaGetDeviceProperties(&prop, device));
+	c->launch.smCount = prop.multiProcessorCount;
+	c->launch.maxSmemOptin = prop.sharedMemPerBlockOptin;
+	CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CKC(cudaEventCreate(&c->evStart));
+	CKC(cudaEventCreate(&c->evStop));
+	CKC(cudaMalloc(&c->accum, px * sizeof(float4)));
+	CKC(cudaMemsetAsync(c->accum, 0, px * sizeof(float4), c->stream));
+	CKC(cudaMalloc(&c->scaledDev, px * sizeof(float4)));
+	CKC(cudaMalloc(&c->ldrDev, px * sizeof(uchar4)));
+	CKC(cudaMallocHost(&c->hostHdr, px * sizeof(float4)));
+	CKC(cudaMallocHost(&c->hostLdr, px * sizeof(uchar4)));
+	CKC(cudaMalloc(&c->counters, kCtrCount * sizeof(unsigned long long)));
+	CKC(cudaMalloc(&c->texDev, kMaxTextures * sizeof(TexDesc)));
+	CKC(cudaMemsetAsync(c->texDev, 0, kMaxTextures * sizeof(TexDesc), c->stream));
+	CKC(cudaStreamSynchronize(c->stream));
+#undef CKC
+	*out = c;
+	return PT_OK;
+}
+
+void pt_destroy(pt_context *c)
+{
+	if (!c) return;
+	cudaSetDevice(c->device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	if (c->ownAccum && c->accum) cudaFree(c->accum);
+	if (c->scaledDev) cudaFree(c->scaledDev);
+	if (c->ldrDev) cudaFree(c->ldrDev);
+	if (c->hostHdr) cudaFreeHost(c->hostHdr);
+	if (c->hostLdr) cudaFreeHost(c->hostLdr);
+	if (c->counters) cudaFree(c->counters);
+	if (c->texDev) cudaFree(c->texDev);
+	if (c->sceneBlob) cudaFree(c->sceneBlob);
+	if (c->mats) cudaFree(c->mats);
+	for (void *p : c->texMem) cudaFree(p);
+	if (c->evStart) cudaEventDestroy(c->evStart);
+	if (c->evStop) cudaEventDestroy(c->evStop);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+int pt_set_scene(pt_context *c, size_t count, const pt_object_desc *objects)
+{
+	if (!c) return setError(PT_E_INVALID, "pt_set_scene: null context");
+	if (count == 0)
+	{
+		printf("Setting an empty scene is not allowed!\n"); // Pathtracer.cpp:115
+		return PT_OK;
+	}
+	if (!objects) return setError(PT_E_INVALID, "pt_set_scene: null objects");
+	CompiledScene cs;
+	std::string err;
+	if (!compileScene(count, objects, c->maxLeaf, cs, err)) return setError(PT_E_LIMIT, "pt_set_scene: " + err);
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	if (c->sceneBlob) { CK(cudaFree(c->sceneBlob)); c->sceneBlob = nullptr; }
+	if (c->mats) { CK(cudaFree(c->mats)); c->mats = nullptr; }
+	const size_t nodeBytes = cs.nodes.size() * sizeof(Node), primBytes = cs.prims.size() * sizeof(Prim);
+	CK(cudaMalloc(&c->sceneBlob, nodeBytes + primBytes));
+	CK(cudaMalloc(&c->mats, cs.mats.size() * sizeof(Mat)));
+	CK(cudaMemcpyAsync(c->sceneBlob, cs.nodes.data(), nodeBytes, cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(reinterpret_cast<char *>(c->sceneBlob) + nodeBytes, cs.prims.data(), primBytes, cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(c->mats, cs.mats.data(), cs.mats.size() * sizeof(Mat), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	c->nodeCount = uint32_t(cs.nodes.size());
+	c->primCount = uint32_t(cs.prims.size());
+	c->bvhDepth = cs.depth;
+	c->stats.bvh_nodes = c->nodeCount;
+	c->stats.bvh_depth = c->bvhDepth;
+	c->stats.scene_bytes = uint32_t(nodeBytes + primBytes + cs.mats.size() * sizeof(Mat));
+	return PT_OK;
+}
+
+uint32_t pt_load_texture_mem(pt_context *c, uint32_t width, uint32_t height, int is_hdr, const void *rgba)
+{
+	if (!c || !rgba || width == 0 || height == 0) return 0;
+	if (c->textureCount >= kMaxTextures) return 0; // Pathtracer.cpp:236-240
+	if (cudaSetDevice(c->device) != cudaSuccess) return 0;
+	const size_t bytes = size_t(width) * height * (is_hdr ? 16 : 4);
+	void *dev = nullptr;
+	if (cudaMalloc(&dev, bytes) != cudaSuccess) { setError(PT_E_CUDA, "pt_load_texture: cudaMalloc failed"); return 0; }
+	if (cudaMemcpyAsync(dev, rgba, bytes, cudaMemcpyHostToDevice, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)
+	{
+		cudaFree(dev);
+		setError(PT_E_CUDA, "pt_load_texture: upload failed");
+		return 0;
+	}
+	TexDesc &t = c->texHost[c->textureCount];
+	t.texels = dev;
+	t.width = width;
+	t.height = height;
+	t.isHdr = is_hdr ? 1u : 0u;
+	t.pad = 0;
+	c->texMem.push_back(dev);
+	if (cudaMemcpyAsync(c->texDev, c->texHost, sizeof c->texHost, cudaMemcpyHostToDevice, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)
+	{
+		setError(PT_E_CUDA, "pt_load_texture: table upload failed");
+		return 0;
+	}
+	return ++c->textureCount;
+}
+
+uint32_t pt_load_texture(pt_context *c, const char *path)
+{
+	if (!c || !path) return 0;
+	if (c->textureCount >= kMaxTextures) return 0;
+	Image img;
+	std::string err;
+	if (!readImage(path, img, err)) { g_lastError = err; return 0; } // failed load -> handle 0, no error (Pathtracer.cpp:253-257)
+	return pt_load_texture_mem(c, img.width, img.height, img.isHdr ? 1 : 0, img.isHdr ? (const void *)img.hdr.data() : (const void *)img.ldr.data());
+}
+
+int pt_set_skybox(pt_context *c, uint32_t handle)
+{
+	if (!c) return setError(PT_E_INVALID, "pt_set_skybox: null context");
+	c->skybox = handle;
+	return PT_OK;
+}
+
+static SceneDev sceneDev(const pt_context *c)
+{
+	SceneDev s;
+	s.sceneBlob = c->sceneBlob;
+	s.mats = c->mats;
+	s.textures = c->texDev;
+	s.nodeCount = c->nodeCount;
+	s.primCount = c->primCount;
+	s.texCount = c->textureCount;
+	s.skybox = (c->skybox <= c->textureCount) ? c->skybox : 0;
+	return s;
+}
+
+int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ignore_history)
+{
+	if (!c || !camera) return setError(PT_E_INVALID, "pt_render: bad arguments");
+	CK(cudaSetDevice(c->device));
+	if (ignore_history)
+	{
+		c->accumulatedFrames = 0; // Pathtracer.cpp:164-167
+		c->totalSamples = 0;
+		c->sampleCursor = c->sampleOffset;
+	}
+	c->timingMs = 0.0f;
+	int launches = 0, usedSmem = 0;
+	CK(cudaMemsetAsync(c->counters, 0, kCtrCount * sizeof(unsigned long long), c->stream));
+	CK(cudaEventRecord(c->evStart, c->stream));
+	const bool run = c->nodeCount >= 1 && c->primCount >= 1 && spp > 0; // Pathtracer.cpp:174
+	if (run)
+	{
+		RenderParams p;
+		p.scene = sceneDev(c);
+		computeCamera(*camera, p.cam);
+		p.accum = c->accum;
+		p.counters = c->counters;
+		p.width = c->width;
+		p.height = c->height;
+		p.spp = spp;
+		p.ignoreHistory = ignore_history ? 1u : 0u;
+		p.sampleOffset = c->sampleCursor;
+		p.sampleStride = c->sampleStride;
+		p.seedLo = uint32_t(c->seed);
+		p.seedHi = uint32_t(c->seed >> 32);
+		p.maxBounces = c->maxBounces;
+		launches = launchTrace(p, c->launch, c->stream, &usedSmem);
+	}
+	CK(cudaEventRecord(c->evStop, c->stream));
+	CK(cudaGetLastError());
+	CK(cudaStreamSynchronize(c->stream));
+	CK(cudaEventElapsedTime(&c->timingMs, c->evStart, c->evStop));
+	if (run)
+	{
+		unsigned long long h[kCtrCount];
+		CK(cudaMemcpy(h, c->counters, sizeof h, cudaMemcpyDeviceToHost));
+		c->stats.samples = (unsigned long long)c->width * c->height * spp;
+		c->stats.rays = h[kCtrRays];
+		c->stats.node_visits = h[kCtrNodes];
+		c->stats.prim_tests = h[kCtrPrims];
+		c->stats.shades = h[kCtrShades];
+		c->stats.misses = h[kCtrMisses];
+		c->stats.scene_in_smem = uint32_t(usedSmem);
+		c->sampleCursor += spp * c->sampleStride;
+		c->totalSamples += spp;
+	}
+	c->stats.gpu_ms = c->timingMs;
+	(void)launches;
+	// the reference counts render() CALLS, not samples (Pathtracer.cpp:226, quirk Q1); "frames_per_spp" = k makes one
+	// call count as ceil(spp / k) calls so a single launch reproduces the reference CLI's 8-spp slicing (main.cpp:271-278)
+	c->accumulatedFrames += (c->framesPerSpp > 0) ? (spp + c->framesPerSpp - 1) / c->framesPerSpp : 1u;
+	return PT_OK;
+}
+
+float pt_get_timing_ms(const pt_context *c) { return c ? c->timingMs : 0.0f; }
+
+static const float *readHdr(pt_context *c, float scale)
+{
+	if (cudaSetDevice(c->device) != cudaSuccess) return nullptr;
+	const uint32_t px = c->width * c->height;
+	launchScale(c->accum, c->scaledDev, px, scale, c->stream);
+	if (cudaMemcpyAsync(c->hostHdr, c->scaledDev, size_t(px) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+	    cudaStreamSynchronize(c->stream) != cudaSuccess)
+	{
+		setError(PT_E_CUDA, std::string("pt_get_hdr: ") + cudaGetErrorString(cudaGetLastError()));
+		return nullptr;
+	}
+	return c->hostHdr;
+}
+
+const float *pt_get_hdr(pt_context *c)
+{
+	if (!c) return nullptr;
+	return readHdr(c, 1.0f / fmaxf(float(c->accumulatedFrames), 1.0f)); // Pathtracer.cpp:307
+}
+
+const float *pt_get_hdr_mean(pt_context *c)
+{
+	if (!c) return nullptr;
+	return readHdr(c, 1.0f / fmaxf(float(c->totalSamples), 1.0f));
+}
+
+const uint8_t *pt_get_ldr(pt_context *c)
+{
+	if (!c) return nullptr;
+	if (cudaSetDevice(c->device) != cudaSuccess) return nullptr;
+	const uint32_t px = c->width * c->height;
+	// tonemap.cu:17 divides by float(accumulatedSampleCount) via reciprocal-multiply; 0 frames -> division by zero in the
+	// reference; here the accumulation is zero in that case and the scale is clamped like getHDRImageData's
+	launchTonemap(c->accum, c->ldrDev, px, 1.0f / fmaxf(float(c->accumulatedFrames), 1.0f), c->stream);
+	if (cudaMemcpyAsync(c->hostLdr, c->ldrDev, size_t(px) * sizeof(uchar4), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+	    cudaStreamSynchronize(c->stream) != cudaSuccess)
+	{
+		setError(PT_E_CUDA, std::string("pt_get_ldr: ") + cudaGetErrorString(cudaGetLastError()));
+		return nullptr;
+	}
+	return c->hostLdr;
+}
+
+int pt_set_option(pt_context *c, const char *key, double value)
+{
+	if (!c || !key) return setError(PT_E_INVALID, "pt_set_option: bad arguments");
+	const std::string k(key);
+	if (k == "seed") c->seed = uint64_t(value);
+	else if (k == "sample_offset") { c->sampleOffset = uint32_t(value); c->sampleCursor = c->sampleOffset; }
+	else if (k == "sample_stride") c->sampleStride = value < 1 ? 1u : uint32_t(value);
+	else if (k == "frames_per_spp") c->framesPerSpp = uint32_t(value);
+	else if (k == "count_work") c->launch.countWork = value != 0;
+	else if (k == "smem_scene") c->launch.smemScene = value != 0;
+	else if (k == "max_bounces") c->maxBounces = value < 1 ? 1u : uint32_t(value);
+	else if (k == "max_leaf") c->maxLeaf = value < 1 ? 1u : uint32_t(value);
+	else if (k == "variant") c->launch.variant = int(value);
+	else return setError(PT_E_INVALID, "pt_set_option: unknown option " + k);
+	return PT_OK;
+}
+
+int pt_get_stats(const pt_context *c, pt_stats *out)
+{
+	if (!c || !out) return setError(PT_E_INVALID, "pt_get_stats: bad arguments");
+	*out = c->stats;
+	return PT_OK;
+}
+
+int pt_primary_pass(pt_context *c, const pt_camera_desc *camera, int32_t *hit_index, float *hit_t)
+{
+	if (!c || !camera || !hit_index || !hit_t) return setError(PT_E_INVALID, "pt_primary_pass: bad arguments");
+	const size_t px = size_t(c->width) * c->height;
+	if (c->nodeCount == 0)
+	{
+		for (size_t i = 0; i < px; ++i) { hit_index[i] = -1; hit_t[i] = 0.0f; }
+		return PT_OK;
+	}
+	CK(cudaSetDevice(c->device));
+	int32_t *dIdx = nullptr;
+	float *dT = nullptr;
+	CK(cudaMalloc(&dIdx, px * 4));
+	CK(cudaMalloc(&dT, px * 4));
+	CameraDev cam;
+	computeCamera(*camera, cam);
+	launchPrimary(sceneDev(c), cam, c->width, c->height, dIdx, dT, c->stream);
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(hit_index, dIdx, px * 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaMemcpyAsync(hit_t, dT, px * 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	CK(cudaFree(dIdx));
+	CK(cudaFree(dT));
+	return PT_OK;
+}
+
+int pt_trace_rays(pt_context *c, size_t n, const float *origins, const float *directions, float t_min, int32_t *hit_index, float *hit_t, float *hit_normal)
+{
+	if (!c || !origins || !directions || !hit_index || !hit_t) return setError(PT_E_INVALID, "pt_trace_rays: bad arguments");
+	if (n == 0) return PT_OK;
+	if (c->nodeCount == 0) return setError(PT_E_INVALID, "pt_trace_rays: no scene");
+	CK(cudaSetDevice(c->device));
+	float *dO = nullptr, *dD = nullptr, *dT = nullptr, *dN = nullptr;
+	int32_t *dI = nullptr;
+	CK(cudaMalloc(&dO, n * 12)); CK(cudaMalloc(&dD, n * 12)); CK(cudaMalloc(&dT, n * 4)); CK(cudaMalloc(&dI, n * 4));
+	if (hit_normal) CK(cudaMalloc(&dN, n * 12));
+	CK(cudaMemcpyAsync(dO, origins, n * 12, cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(dD, directions, n * 12, cudaMemcpyHostToDevice, c->stream));
+	launchTraceRays(sceneDev(c), n, dO, dD, t_min, dI, dT, dN, c->stream);
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(hit_index, dI, n * 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaMemcpyAsync(hit_t, dT, n * 4, cudaMemcpyDeviceToHost, c->stream));
+	if (hit_normal) CK(cudaMemcpyAsync(hit_normal, dN, n * 12, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	cudaFree(dO); cudaFree(dD); cudaFree(dT); cudaFree(dI);
+	if (dN) cudaFree(dN);
+	return PT_OK;
+}
+
+void *pt_accum_device_ptr(pt_context *c) { return c ? (void *)c->accum : nullptr; }
+
+int pt_set_accum_device_ptr(pt_context *c, void *device_ptr)
+{
+	if (!c || !device_ptr) return setError(PT_E_INVALID, "pt_set_accum_device_ptr: bad arguments");
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	if (c->ownAccum && c->accum) CK(cudaFree(c->accum));
+	c->accum = reinterpret_cast<float4 *>(device_ptr);
+	c->ownAccum = false;
+	return PT_OK;
+}
+
+int pt_parse_scene_file(const char *json_path, pt_object_desc *objects, size_t capacity, pt_camera_desc *camera_out, float aspect, char *tex_paths,
+                        size_t tex_paths_cap, int32_t *skybox_tex_index)
+{
+	if (!json_path) return setError(PT_E_INVALID, "pt_parse_scene_file: null path");
+	ParsedScene ps;
+	std::string err;
+	int code = PT_E_PARSE;
+	if (!parseSceneFile(json_path, aspect, ps, err, &code)) return setError(code, err);
+	if (objects)
+		for (size_t i = 0; i < ps.objects.size() && i < capacity; ++i) objects[i] = ps.objects[i];
+	if (camera_out) *camera_out = ps.camera;
+	if (skybox_tex_index) *skybox_tex_index = int32_t(ps.skyboxTexture);
+	if (tex_paths && tex_paths_cap)
+	{
+		std::string joined;
+		for (size_t i = 0; i < ps.texturePaths.size(); ++i) { if (i) joined += '\n'; joined += ps.texturePaths[i]; }
+		snprintf(tex_paths, tex_paths_cap, "%s", joined.c_str());
+	}
+	return int(ps.objects.size());
+}
+
+int pt_load_scene_file(pt_context *c, const char *json_path, pt_camera_desc *camera_out)
+{
+	if (!c || !json_path) return setError(PT_E_INVALID, "pt_load_scene_file: bad arguments");
+	ParsedScene ps;
+	std::string err;
+	int code = PT_E_PARSE;
+	if (!parseSceneFile(json_path, float(c->width) / float(c->height), ps, err, &code)) return setError(code, err);
+	for (const std::string &m : ps.messages) printf("%s\n", m.c_str());
+	// textures load in first-use order; a failed load maps to handle 0 and does not consume a slot (SceneLoader.cpp:127-149)
+	std::vector<uint32_t> handles(ps.texturePaths.size(), 0);
+	auto loadIdx = [&](uint32_t idx) -> uint32_t { return idx == 0 ? 0u : handles[idx - 1]; };
+	size_t objectTexCount = ps.texturePaths.size();
+	if (ps.skyboxTexture != 0 && ps.skyboxTexture == ps.texturePaths.size())
+	{
+		// the skybox path may be new (last entry) - it is loaded after setScene in the reference; handle order is the same
+	}
+	for (size_t i = 0; i < objectTexCount; ++i) handles[i] = pt_load_texture(c, ps.texturePaths[i].c_str());
+	for (pt_object_desc &o : ps.objects) o.material.texture = loadIdx(o.material.texture);
+	if (ps.hasObjectsArray)
+	{
+		const int r = pt_set_scene(c, ps.objects.size(), ps.objects.data());
+		if (r != PT_OK) return r;
+	}
+	if (ps.skyboxTexture != 0 || true)
+	{
+		// setSkyboxTextureHandle is only called when "skybox" is a string (SceneLoader.cpp:329-332); handle 0 otherwise
+		if (ps.skyboxTexture != 0) pt_set_skybox(c, loadIdx(ps.skyboxTexture));
+	}
+	if (camera_out) *camera_out = ps.camera;
+	return PT_OK;
+}
+
+int pt_write_png(const char *path, uint32_t width, uint32_t height, const uint8_t *rgba)
+{
+	std::string err;
+	if (!path || !rgba) return setError(PT_E_INVALID, "pt_write_png: bad arguments");
+	if (!writePng(path, width, height, rgba, err)) return setError(PT_E_IO, err);
+	return PT_OK;
+}
+
+int pt_write_hdr(const char *path, uint32_t width, uint32_t height, const float *rgba)
+{
+	std::string err;
+	if (!path || !rgba) return setError(PT_E_INVALID, "pt_write_hdr: bad arguments");
+	if (!writeHdr(path, width, height, rgba, err)) return setError(PT_E_IO, err);
+	return PT_OK;
+}
+
+int pt_read_image(const char *path, uint32_t *width, uint32_t *height, int *is_hdr, void **rgba)
+{
+	if (!path || !width || !height || !is_hdr || !rgba) return setError(PT_E_INVALID, "pt_read_image: bad arguments");
+	Image img;
+	std::string err;
+	if (!readImage(path, img, err)) return setError(PT_E_IO, err);
+	*width = img.width;
+	*height = img.height;
+	*is_hdr = img.isHdr ? 1 : 0;
+	const size_t bytes = size_t(img.width) * img.height * (img.isHdr ? 16 : 4);
+	*rgba = malloc(bytes);
+	if (!*rgba) return setError(PT_E_LIMIT, "pt_read_image: out of memory");
+	memcpy(*rgba, img.isHdr ? (const void *)img.hdr.data() : (const void *)img.ldr.data(), bytes);
+	return PT_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,80 @@
+// pt_types.h — device-side data layout shared by the host scene compiler and the CUDA kernels.
+// All records are multiples of 16 bytes so every access is a 128-bit load (LDS.128 from the shared-memory copy,
+// LDG.E.128.CONSTANT from HBM/L2 for scenes that do not fit).
+#pragma once
+#include <cstdint>
+
+namespace ptb
+{
+
+// One BVH node = the boxes of BOTH children + their references (64 B, one 128-bit x4 fetch tests two boxes).
+// Replaces the reference's 32 B single-box node (BVH.h:6-11), whose traversal needs one dependent fetch per box.
+//   f[0..5]  = child0 min.xyz, max.xyz      f[6..11] = child1 min.xyz, max.xyz
+//   child[k] >= 0 : index of an interior node
+//   child[k] <  0 : leaf; bits 0..23 = first primitive (BVH order), bits 24..27 = primitive count (1..15),
+//                   bits 28..30 = shape type of the first primitive (lets the scheduler bin the next intersection
+//                   by shape class without touching memory)
+//   an EMPTY child has child = kEmptyChild and an inverted box (never hit)
+struct alignas(16) Node
+{
+	float f[12];
+	int32_t child[2];
+	uint32_t pad[2];
+};
+static_assert(sizeof(Node) == 64, "Node must be 64 bytes");
+
+constexpr int32_t kLeafBit = int32_t(0x80000000u);
+constexpr int kLeafCountShift = 24;
+constexpr int kLeafTypeShift = 28;
+constexpr uint32_t kLeafStartMask = (1u << kLeafCountShift) - 1u;
+constexpr int32_t kEmptyChild = kLeafBit; // leaf with count 0
+constexpr uint32_t kMaxLeafPrims = 15;
+constexpr int kStackSize = 48;
+
+// One primitive = world->local 3x4 (the reference's Hittable rows, Hittable.h:22-24) + shape type + indices (64 B).
+// The 40 B material the reference embeds in every 96 B Hittable (Hittable.h:25) lives in its own table: it is
+// only needed once per path segment (at the closest hit), not once per candidate.
+struct alignas(16) Prim
+{
+	float row0[4];
+	float row1[4];
+	float row2[4];
+	uint32_t type;       // PT_SPHERE .. PT_CUBE
+	uint32_t sceneIndex; // index in the caller's object array (tie-break + primary-pass output)
+	uint32_t flags;      // bit0: textured (needs u,v)
+	uint32_t pad;
+};
+static_assert(sizeof(Prim) == 64, "Prim must be 64 bytes");
+
+// Material (reference Material.h:22-27, 40 B) padded to 48 B, with roughness already clamped (Material.inl:12).
+struct alignas(16) Mat
+{
+	float baseColor[3];
+	float roughness;
+	float emissive[3];
+	float metalness;
+	uint32_t texture; // 1-based handle, 0 = none
+	uint32_t type;    // PT_LAMBERT / PT_GGX / PT_LAMBERT_GGX
+	uint32_t pad[2];
+};
+static_assert(sizeof(Mat) == 48, "Mat must be 48 bytes");
+
+// Packed texture descriptor for the read-only path: LDR = RGBA8 (one 32-bit texel), HDR = float4 (one 128-bit texel)
+struct TexDesc
+{
+	const void *texels;
+	uint32_t width;
+	uint32_t height;
+	uint32_t isHdr;
+	uint32_t pad;
+};
+
+struct CameraDev
+{
+	float origin[3];
+	float lowerLeft[3];
+	float horizontal[3];
+	float vertical[3];
+};
+
+} // namespace ptb

@@ -1,0 +1,352 @@
+// scene_compile.cpp — host scene compiler (see scene_compile.h).
+//
+// What it replaces in the reference: CpuHittable's ctor (Hittable.cpp:115-179), BVH::build (BVH.cpp:66-228) and the
+// Hittable/BVHNode upload format (Pathtracer.cpp:125-155).  The transform arithmetic keeps the reference's float
+// operation order (this file is compiled with -ffp-contract=off) because the world->local rows feed straight into
+// the hit distance t that the parity gate compares; everything else (tree builder, node format) is our own design:
+// 16-bin SAH over centroid bounds, leaves chosen by cost, two-box 64-byte nodes, separate material table.
+#include "scene_compile.h"
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+namespace ptb
+{
+
+namespace
+{
+struct V3 { float x, y, z; };
+inline float dot3(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+void quatToRotMat(const float q[4], float m[3][3])
+{
+	const float x = q[0], y = q[1], z = q[2], w = q[3];
+	const float xx = x * x, yy = y * y, zz = z * z, xz = x * z, xy = x * y, yz = y * z, wx = w * x, wy = w * y, wz = w * z;
+	m[0][0] = 1.0f - 2.0f * (yy + zz); m[0][1] = 2.0f * (xy + wz); m[0][2] = 2.0f * (xz - wy);
+	m[1][0] = 2.0f * (xy - wz); m[1][1] = 1.0f - 2.0f * (xx + zz); m[1][2] = 2.0f * (yz + wx);
+	m[2][0] = 2.0f * (xz + wy); m[2][1] = 2.0f * (yz - wx); m[2][2] = 1.0f - 2.0f * (xx + yy);
+}
+} // namespace
+
+void computeObjectXform(const pt_object_desc &d, ObjectXform &o)
+{
+	V3 scale = { d.scale[0], d.scale[1], d.scale[2] };
+	if (d.type == PT_DISK || d.type == PT_QUAD)
+	{
+		scale.y = 1.0f; // flat shapes ignore their y scale (Hittable.cpp:124-128)
+	}
+	const V3 pos = { d.position[0], d.position[1], d.position[2] };
+
+	// Euler XYZ (radians) -> quaternion -> rotation; inverse via the conjugate (Hittable.cpp:33-56)
+	const float hx = d.rotation[0] * 0.5f, hy = d.rotation[1] * 0.5f, hz = d.rotation[2] * 0.5f;
+	const float cx = cosf(hx), cy = cosf(hy), cz = cosf(hz), sx = sinf(hx), sy = sinf(hy), sz = sinf(hz);
+	float q[4], qi[4];
+	q[3] = cx * cy * cz + sx * sy * sz;
+	q[0] = sx * cy * cz - cx * sy * sz;
+	q[1] = cx * sy * cz + sx * cy * sz;
+	q[2] = cx * cy * sz - sx * sy * cz;
+	const float invDot = 1.0f / (q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+	qi[0] = -q[0] * invDot; qi[1] = -q[1] * invDot; qi[2] = -q[2] * invDot; qi[3] = q[3] * invDot;
+
+	float rInv[3][3], r[3][3];
+	quatToRotMat(qi, rInv);
+	quatToRotMat(q, r);
+	const float invS[3] = { 1.0f / scale.x, 1.0f / scale.y, 1.0f / scale.z };
+	const V3 npos = { -pos.x, -pos.y, -pos.z };
+	for (int k = 0; k < 3; ++k) // world->local = S^-1 R^-1 T^-1 (Hittable.cpp:59-79)
+	{
+		o.w2l[k][0] = invS[k] * rInv[0][k];
+		o.w2l[k][1] = invS[k] * rInv[1][k];
+		o.w2l[k][2] = invS[k] * rInv[2][k];
+		o.w2l[k][3] = invS[k] * dot3(V3{ rInv[0][k], rInv[1][k], rInv[2][k] }, npos);
+	}
+	const float p[3] = { pos.x, pos.y, pos.z };
+	for (int k = 0; k < 3; ++k) // local->world = T R S (Hittable.cpp:82-102)
+	{
+		o.l2w[k][0] = scale.x * r[0][k];
+		o.l2w[k][1] = scale.y * r[1][k];
+		o.l2w[k][2] = scale.z * r[2][k];
+		o.l2w[k][3] = p[k];
+	}
+
+	// world AABB of the 8 corners of the per-type local extent (Hittable.cpp:139-178)
+	float ye[2] = { -1.0f, 1.0f };
+	if (d.type == PT_DISK || d.type == PT_QUAD) { ye[0] = -0.01f; ye[1] = 0.01f; }
+	else if (d.type == PT_PARABOLOID) { ye[0] = 0.0f; }
+	const float xe[2] = { -1.0f, 1.0f }, ze[2] = { -1.0f, 1.0f };
+	for (int k = 0; k < 3; ++k) { o.bmin[k] = FLT_MAX; o.bmax[k] = -FLT_MAX; }
+	for (int z = 0; z < 2; ++z) for (int y = 0; y < 2; ++y) for (int x = 0; x < 2; ++x)
+	{
+		const V3 c = { xe[x], ye[y], ze[z] };
+		for (int k = 0; k < 3; ++k)
+		{
+			const float w = dot3(c, V3{ o.l2w[k][0], o.l2w[k][1], o.l2w[k][2] }) + o.l2w[k][3];
+			o.bmin[k] = o.bmin[k] < w ? o.bmin[k] : w;
+			o.bmax[k] = o.bmax[k] >= w ? o.bmax[k] : w;
+		}
+	}
+}
+
+void computeCamera(const pt_camera_desc &c, CameraDev &out)
+{
+	auto norm = [](V3 v) { const float inv = 1.0f / sqrtf(v.x * v.x + v.y * v.y + v.z * v.z); return V3{ inv * v.x, inv * v.y, inv * v.z }; };
+	auto cross = [](V3 u, V3 v) { return V3{ u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x }; };
+	const float tanHalf = tanf(c.fovy * 0.5f);
+	const V3 origin = { c.position[0], c.position[1], c.position[2] };
+	const V3 backward = norm(V3{ origin.x - c.look_at[0], origin.y - c.look_at[1], origin.z - c.look_at[2] });
+	const V3 right = norm(cross(V3{ c.up[0], c.up[1], c.up[2] }, backward));
+	const V3 up = cross(backward, right);
+	const float halfH = tanHalf, halfW = c.aspect * halfH;
+	// lowerLeft = -halfW*right + -halfH*up - backward; horizontal = 2*halfW*right; vertical = 2*halfH*up
+	const float a = -halfW, b = -halfH, h2 = 2.0f * halfW, v2 = 2.0f * halfH;
+	const float r[3] = { right.x, right.y, right.z }, u[3] = { up.x, up.y, up.z }, bw[3] = { backward.x, backward.y, backward.z };
+	const float o[3] = { origin.x, origin.y, origin.z };
+	for (int k = 0; k < 3; ++k)
+	{
+		out.origin[k] = o[k];
+		out.lowerLeft[k] = (a * r[k] + b * u[k]) - bw[k];
+		out.horizontal[k] = h2 * r[k];
+		out.vertical[k] = v2 * u[k];
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// BVH build
+// ---------------------------------------------------------------------------------------------------------------
+namespace
+{
+constexpr int kBins = 16;
+constexpr float kTraversalCost = 1.0f; // cost of one two-box node fetch + test, in units of...
+constexpr float kPrimCost = 1.5f;      // ...one primitive intersection (quadric tests are dearer than slab tests)
+
+struct Box
+{
+	float mn[3], mx[3];
+	void reset() { for (int k = 0; k < 3; ++k) { mn[k] = FLT_MAX; mx[k] = -FLT_MAX; } }
+	void grow(const Box &b) { for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], b.mn[k]); mx[k] = std::max(mx[k], b.mx[k]); } }
+	void growPoint(const float *p) { for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], p[k]); mx[k] = std::max(mx[k], p[k]); } }
+	float area() const
+	{
+		const float e[3] = { mx[0] - mn[0], mx[1] - mn[1], mx[2] - mn[2] };
+		if (e[0] < 0.0f || e[1] < 0.0f || e[2] < 0.0f) return 0.0f;
+		return 2.0f * (e[0] * e[1] + e[0] * e[2] + e[1] * e[2]);
+	}
+};
+
+struct BuildPrim
+{
+	Box box;
+	float c[3];
+	uint32_t index;
+};
+
+struct Builder
+{
+	std::vector<BuildPrim> &bp;
+	std::vector<Node> &nodes;
+	std::atomic<uint32_t> nextNode{ 0 };
+	std::atomic<uint32_t> leafCount{ 0 };
+	uint32_t maxLeaf;
+	const pt_object_desc *objects;
+
+	Builder(std::vector<BuildPrim> &b, std::vector<Node> &n, uint32_t ml, const pt_object_desc *o) : bp(b), nodes(n), maxLeaf(ml), objects(o) {}
+
+	int32_t leafRef(size_t begin, size_t count) const
+	{
+		const uint32_t t = objects[bp[begin].index].type <= PT_CUBE ? objects[bp[begin].index].type : uint32_t(PT_SPHERE);
+		return int32_t(0x80000000u | (t << kLeafTypeShift) | (uint32_t(count) << kLeafCountShift) | uint32_t(begin));
+	}
+
+	// returns the child reference for [begin,end), its box in `box`, and the interior depth below it in `depth`
+	int32_t build(size_t begin, size_t end, Box &box, uint32_t &depth)
+	{
+		const size_t n = end - begin;
+		Box cb;
+		box.reset();
+		cb.reset();
+		for (size_t i = begin; i < end; ++i) { box.grow(bp[i].box); cb.growPoint(bp[i].c); }
+		if (n == 1)
+		{
+			depth = 0;
+			leafCount++;
+			return leafRef(begin, n);
+		}
+
+		// binned SAH over the centroid bounds
+		int bestAxis = -1, bestBin = -1;
+		float bestCost = FLT_MAX;
+		const float parentArea = std::max(box.area(), 1e-30f);
+		for (int axis = 0; axis < 3; ++axis)
+		{
+			const float ext = cb.mx[axis] - cb.mn[axis];
+			if (!(ext > 0.0f)) continue;
+			Box bins[kBins];
+			uint32_t counts[kBins] = {};
+			for (auto &b : bins) b.reset();
+			const float k = float(kBins) / ext;
+			for (size_t i = begin; i < end; ++i)
+			{
+				int b = int((bp[i].c[axis] - cb.mn[axis]) * k);
+				b = b < 0 ? 0 : (b > kBins - 1 ? kBins - 1 : b);
+				counts[b]++;
+				bins[b].grow(bp[i].box);
+			}
+			float rightArea[kBins];
+			uint32_t rightCount[kBins];
+			Box acc;
+			acc.reset();
+			uint32_t cnt = 0;
+			for (int b = kBins - 1; b > 0; --b) { acc.grow(bins[b]); cnt += counts[b]; rightArea[b] = acc.area(); rightCount[b] = cnt; }
+			acc.reset();
+			cnt = 0;
+			for (int b = 0; b < kBins - 1; ++b)
+			{
+				acc.grow(bins[b]);
+				cnt += counts[b];
+				if (cnt == 0 || rightCount[b + 1] == 0) continue;
+				const float cost = kTraversalCost + kPrimCost * (float(cnt) * acc.area() + float(rightCount[b + 1]) * rightArea[b + 1]) / parentArea;
+				if (cost < bestCost) { bestCost = cost; bestAxis = axis; bestBin = b; }
+			}
+		}
+
+		if (n <= maxLeaf && (bestAxis < 0 || bestCost >= kPrimCost * float(n)))
+		{
+			depth = 0;
+			leafCount++;
+			return leafRef(begin, n);
+		}
+
+		size_t mid = begin;
+		if (bestAxis >= 0)
+		{
+			const float ext = cb.mx[bestAxis] - cb.mn[bestAxis];
+			const float k = float(kBins) / ext, lo = cb.mn[bestAxis];
+			const int axis = bestAxis, bin = bestBin;
+			auto it = std::partition(bp.begin() + begin, bp.begin() + end, [=](const BuildPrim &p)
+				{
+					int b = int((p.c[axis] - lo) * k);
+					b = b < 0 ? 0 : (b > kBins - 1 ? kBins - 1 : b);
+					return b <= bin;
+				});
+			mid = size_t(it - bp.begin());
+		}
+		if (mid == begin || mid == end)
+		{
+			// all centroids coincide (or binning failed): split the range in the middle by index along the widest axis
+			int axis = 0;
+			const float e[3] = { box.mx[0] - box.mn[0], box.mx[1] - box.mn[1], box.mx[2] - box.mn[2] };
+			if (e[1] > e[axis]) axis = 1;
+			if (e[2] > e[axis]) axis = 2;
+			mid = (begin + end) / 2;
+			std::nth_element(bp.begin() + begin, bp.begin() + mid, bp.begin() + end, [axis](const BuildPrim &a, const BuildPrim &b)
+				{ return a.c[axis] < b.c[axis] || (a.c[axis] == b.c[axis] && a.index < b.index); });
+		}
+
+		const uint32_t nodeIndex = nextNode++;
+		Box lb, rb;
+		uint32_t ld = 0, rd = 0;
+		int32_t lc, rc;
+		if (n > 8192)
+		{
+#pragma omp task shared(lb, ld, lc) default(shared)
+			lc = build(begin, mid, lb, ld);
+			rc = build(mid, end, rb, rd);
+#pragma omp taskwait
+		}
+		else
+		{
+			lc = build(begin, mid, lb, ld);
+			rc = build(mid, end, rb, rd);
+		}
+		Node &nd = nodes[nodeIndex];
+		for (int k = 0; k < 3; ++k) { nd.f[k] = lb.mn[k]; nd.f[3 + k] = lb.mx[k]; nd.f[6 + k] = rb.mn[k]; nd.f[9 + k] = rb.mx[k]; }
+		nd.child[0] = lc;
+		nd.child[1] = rc;
+		nd.pad[0] = nd.pad[1] = 0;
+		depth = 1 + std::max(ld, rd);
+		return int32_t(nodeIndex);
+	}
+};
+} // namespace
+
+bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf, CompiledScene &out, std::string &err)
+{
+	out = CompiledScene();
+	if (count == 0) { err = "empty scene"; return false; }
+	if (count > kLeafStartMask) { err = "too many objects"; return false; }
+	maxLeaf = std::max(1u, std::min(maxLeaf, kMaxLeafPrims));
+
+	std::vector<ObjectXform> xf(count);
+	std::vector<BuildPrim> bp(count);
+#pragma omp parallel for schedule(static) if (count > 4096)
+	for (long i = 0; i < long(count); ++i)
+	{
+		computeObjectXform(objects[i], xf[i]);
+		for (int k = 0; k < 3; ++k)
+		{
+			bp[i].box.mn[k] = xf[i].bmin[k];
+			bp[i].box.mx[k] = xf[i].bmax[k];
+			bp[i].c[k] = 0.5f * (xf[i].bmin[k] + xf[i].bmax[k]);
+		}
+		bp[i].index = uint32_t(i);
+	}
+
+	out.nodes.assign(std::max<size_t>(count, 2) - 1 + 1, Node());
+	Builder b(bp, out.nodes, maxLeaf, objects);
+	Box rootBox;
+	uint32_t depth = 0;
+	int32_t root;
+#pragma omp parallel if (count > 8192)
+#pragma omp single
+	root = b.build(0, count, rootBox, depth);
+
+	if (root < 0)
+	{
+		// the whole scene is one leaf: give it a root node whose second child is empty
+		Node &nd = out.nodes[0];
+		for (int k = 0; k < 3; ++k) { nd.f[k] = rootBox.mn[k]; nd.f[3 + k] = rootBox.mx[k]; nd.f[6 + k] = FLT_MAX; nd.f[9 + k] = -FLT_MAX; }
+		nd.child[0] = root;
+		nd.child[1] = kEmptyChild;
+		b.nextNode = 1;
+		depth = 1;
+	}
+	else if (root != 0)
+	{
+		err = "internal: root is not node 0";
+		return false;
+	}
+	out.nodes.resize(b.nextNode.load());
+	out.depth = depth;
+	out.leafCount = b.leafCount.load();
+	for (int k = 0; k < 3; ++k) { out.sceneMin[k] = rootBox.mn[k]; out.sceneMax[k] = rootBox.mx[k]; }
+	if (depth + 2 > uint32_t(kStackSize)) { err = "BVH deeper than the traversal stack"; return false; }
+
+	out.prims.resize(count);
+	out.mats.resize(count);
+	for (size_t i = 0; i < count; ++i)
+	{
+		const uint32_t src = bp[i].index;
+		const pt_object_desc &d = objects[src];
+		Prim &p = out.prims[i];
+		memcpy(p.row0, xf[src].w2l[0], 16);
+		memcpy(p.row1, xf[src].w2l[1], 16);
+		memcpy(p.row2, xf[src].w2l[2], 16);
+		p.type = d.type <= PT_CUBE ? d.type : uint32_t(PT_SPHERE);
+		p.sceneIndex = src;
+		p.flags = d.material.texture != 0 ? 1u : 0u;
+		p.pad = 0;
+		Mat &m = out.mats[i];
+		memcpy(m.baseColor, d.material.base_color, 12);
+		memcpy(m.emissive, d.material.emissive, 12);
+		m.roughness = d.material.roughness < 0.04f ? 0.04f : d.material.roughness; // Material.inl:12
+		m.metalness = d.material.metalness;
+		m.texture = d.material.texture;
+		m.type = d.material.type <= PT_LAMBERT_GGX ? d.material.type : uint32_t(PT_LAMBERT);
+		m.pad[0] = m.pad[1] = 0;
+	}
+	return true;
+}
+
+} // namespace ptb

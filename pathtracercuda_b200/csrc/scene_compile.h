@@ -1,0 +1,40 @@
+// scene_compile.h — host scene compiler: object descriptions -> flat device arrays (nodes, primitives, materials).
+#pragma once
+#include "../../include/pt_b200.h"
+#include "pt_types.h"
+#include <string>
+#include <vector>
+
+namespace ptb
+{
+
+struct CompiledScene
+{
+	std::vector<Node> nodes;
+	std::vector<Prim> prims; // BVH order
+	std::vector<Mat> mats;   // BVH order (parallel to prims)
+	uint32_t depth = 0;      // interior-node depth (max traversal stack = depth)
+	uint32_t leafCount = 0;
+	float sceneMin[3] = { 0, 0, 0 };
+	float sceneMax[3] = { 0, 0, 0 };
+};
+
+struct ObjectXform
+{
+	float w2l[3][4]; // world -> local rows
+	float l2w[3][4]; // local -> world rows
+	float bmin[3], bmax[3];
+};
+
+// CpuHittable ctor equivalent (reference Hittable.cpp:115-179): rows + world AABB, float arithmetic in the
+// reference's operation order so the rows are bit-identical to the reference's.
+void computeObjectXform(const pt_object_desc &d, ObjectXform &out);
+
+// Build the BVH (binned SAH, kBins bins, centroid bounds, leaf when cheaper) and flatten it.
+// maxLeaf in [1, kMaxLeafPrims].  Returns false and sets err on failure (depth over kStackSize).
+bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf, CompiledScene &out, std::string &err);
+
+// Camera ctor + update() equivalent (reference Camera.inl:4-23,54-62)
+void computeCamera(const pt_camera_desc &c, CameraDev &out);
+
+} // namespace ptb

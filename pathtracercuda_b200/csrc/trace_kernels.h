@@ -1,0 +1,49 @@
+// trace_kernels.h — launch interface of the CUDA trace path (implemented in trace_kernels.cu).
+#pragma once
+#include "pt_types.h"
+#include <cuda_runtime.h>
+
+namespace ptb
+{
+
+// counters[] layout (device, unsigned long long)
+enum { kCtrWork = 0, kCtrRays = 1, kCtrNodes = 2, kCtrPrims = 3, kCtrShades = 4, kCtrMisses = 5, kCtrCount = 8 };
+
+struct SceneDev
+{
+	const float4 *sceneBlob = nullptr; // [nodes | prims], 16-byte records, one allocation (bulk-copied to smem)
+	const Mat *mats = nullptr;
+	const TexDesc *textures = nullptr;
+	uint32_t nodeCount = 0, primCount = 0, texCount = 0, skybox = 0;
+};
+
+struct RenderParams
+{
+	SceneDev scene;
+	CameraDev cam;
+	float4 *accum;
+	unsigned long long *counters;
+	uint32_t width, height, spp, ignoreHistory;
+	uint32_t sampleOffset, sampleStride;
+	uint32_t seedLo, seedHi;
+	uint32_t maxBounces;
+};
+
+struct LaunchConfig
+{
+	int smCount = 148;
+	int smemScene = 1;   // stage the scene in shared memory when it fits
+	int countWork = 0;   // node/prim/shade/miss counters
+	int variant = 0;     // kernel variant (0 = default)
+	size_t maxSmemOptin = 0;
+};
+
+// Returns the number of kernels launched; *usedSmem = 1 when the scene was staged in shared memory.
+int launchTrace(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t stream, int *usedSmem);
+int launchPrimary(const SceneDev &scene, const CameraDev &cam, uint32_t width, uint32_t height, int32_t *hitIndex, float *hitT, cudaStream_t stream);
+int launchTraceRays(const SceneDev &scene, size_t n, const float *origins, const float *directions, float tMin, int32_t *hitIndex, float *hitT,
+                    float *hitNormal, cudaStream_t stream);
+int launchTonemap(const float4 *accum, uchar4 *out, uint32_t pixels, float invSampleCount, cudaStream_t stream);
+int launchScale(const float4 *accum, float4 *out, uint32_t pixels, float scale, cudaStream_t stream);
+
+} // namespace ptb
