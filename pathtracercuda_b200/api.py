@@ -7,7 +7,7 @@ import numpy as np
 
 from .abi import CameraDesc, ObjectDesc, Stats, object_array
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpt_b200.so")
+LIB_PATH = os.environ.get("PT_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libpt_b200.so")
 _lib = None
 
 

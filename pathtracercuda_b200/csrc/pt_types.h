@@ -14,7 +14,7 @@ namespace ptb
 //   child[k] <  0 : leaf; bits 0..23 = first primitive (BVH order), bits 24..27 = primitive count (1..15),
 //                   bits 28..30 = shape type of the first primitive (lets the scheduler bin the next intersection
 //                   by shape class without touching memory)
-//   an EMPTY child has child = kEmptyChild and an inverted box (never hit)
+//   an EMPTY child has child = kEmptyChild and a degenerate box at +FLT_MAX (never hit)
 struct alignas(16) Node
 {
 	float f[12];

@@ -306,7 +306,9 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 	{
 		// the whole scene is one leaf: give it a root node whose second child is empty
 		Node &nd = out.nodes[0];
-		for (int k = 0; k < 3; ++k) { nd.f[k] = rootBox.mn[k]; nd.f[3 + k] = rootBox.mx[k]; nd.f[6 + k] = FLT_MAX; nd.f[9 + k] = -FLT_MAX; }
+		// the empty child's box is a point at +FLT_MAX: its slab interval is degenerate (near == far) for every ray, so the
+		// strict near < far test never passes.  (An inverted box would NOT work: the min/max slab test un-inverts it.)
+		for (int k = 0; k < 3; ++k) { nd.f[k] = rootBox.mn[k]; nd.f[3 + k] = rootBox.mx[k]; nd.f[6 + k] = FLT_MAX; nd.f[9 + k] = FLT_MAX; }
 		nd.child[0] = root;
 		nd.child[1] = kEmptyChild;
 		b.nextNode = 1;

@@ -81,7 +81,6 @@ __global__ void __launch_bounds__(kThreads, 3) traceKernel(const RenderParams p)
 
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t totalPixels = p.width * p.height;
-	const float invW = 1.0f / float(p.width), invH = 1.0f / float(p.height);
 	const V3 camO = mk(p.cam.origin[0], p.cam.origin[1], p.cam.origin[2]);
 
 	uint32_t pixel = kInvalid, sample = p.spp;
@@ -129,8 +128,8 @@ __global__ void __launch_bounds__(kThreads, 3) traceKernel(const RenderParams p)
 				sampleIdx = p.sampleOffset + sample * p.sampleStride;
 				const uint4 r = philox4x32_10(pixel, sampleIdx, 0u, 0u, p.seedLo, p.seedHi);
 				const uint32_t px = pixel % p.width, py = pixel / p.width;
-				const float u = (float(px) + uniform01(r.x)) * invW; // (x + U) / float(width): reciprocal-multiply like vec3's operator/
-				const float v = (float(py) + uniform01(r.y)) * invH;
+				const float u = divExact(float(px) + uniform01(r.x), float(p.width)); // trace.cu:190
+				const float v = divExact(float(py) + uniform01(r.y), float(p.height));
 				rz = r.z; rw = r.w;
 				ro = camO;
 				rd = cameraDir(p.cam, u, v);
@@ -258,7 +257,6 @@ __global__ void __launch_bounds__(kThreads, 3) traceKernelV2(const RenderParams 
 
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t totalPixels = p.width * p.height;
-	const float invW = 1.0f / float(p.width), invH = 1.0f / float(p.height);
 	const V3 camO = mk(p.cam.origin[0], p.cam.origin[1], p.cam.origin[2]);
 	constexpr float tMin = 0.001f;
 
@@ -273,6 +271,7 @@ __global__ void __launch_bounds__(kThreads, 3) traceKernelV2(const RenderParams 
 	int primBest = -1, cur = 0, sp = 0;
 	uint32_t sceneBest = 0, leafPrim = 0, leafLeft = 0;
 	int stack[kStackSize];
+	stack[0] = kSentinel;
 	uint32_t rays = 0, nodeVisits = 0, primTests = 0, shades = 0, misses = 0;
 
 	auto setCur = [&](int c)
@@ -289,6 +288,7 @@ __global__ void __launch_bounds__(kThreads, 3) traceKernelV2(const RenderParams 
 			leafPrim = uint32_t(c) & kLeafStartMask;
 			leafLeft = (uint32_t(c) >> kLeafCountShift) & 15u;
 			want = classOfType((uint32_t(c) >> kLeafTypeShift) & 7u);
+			if (leafLeft == 0u) { cur = kSentinel; pendingMiss = primBest < 0; want = pendingMiss ? W_GEN : W_SHADE; } // empty leaf: never referenced by a hit box
 		}
 	};
 	auto pop = [&]() -> int { return sp > 0 ? stack[--sp] : kSentinel; };
@@ -484,8 +484,8 @@ __global__ void __launch_bounds__(kThreads, 3) traceKernelV2(const RenderParams 
 				sampleIdx = p.sampleOffset + sample * p.sampleStride;
 				const uint4 r = philox4x32_10(pixel, sampleIdx, 0u, 0u, p.seedLo, p.seedHi);
 				const uint32_t px = pixel % p.width, py = pixel / p.width;
-				const float u = (float(px) + uniform01(r.x)) * invW;
-				const float v = (float(py) + uniform01(r.y)) * invH;
+				const float u = divExact(float(px) + uniform01(r.x), float(p.width));
+				const float v = divExact(float(py) + uniform01(r.y), float(p.height));
 				rz = r.z; rw = r.w;
 				ro = camO;
 				rd = cameraDir(p.cam, u, v);
@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(kThreads) primaryKernel(SceneDev scene, Camera
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
 	{
 		const uint32_t x = i % width, y = i / width;
-		const float u = (float(x) + 0.5f) / float(width), v = (float(y) + 0.5f) / float(height);
+		const float u = divExact(float(x) + 0.5f, float(width)), v = divExact(float(y) + 0.5f, float(height));
 		const V3 o = mk(cam.origin[0], cam.origin[1], cam.origin[2]);
 		const V3 d = cameraDir(cam, u, v);
 		const Hit h = closestHit<false, false>(sv, o, d, 0.001f, nv, pt);
@@ -610,12 +610,11 @@ int launchTrace(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t str
 	      : (cfg.countWork ? launchKernel(KERN<false, true __VA_ARGS__>, p, cfg, sb, stream) : launchKernel(KERN<false, false __VA_ARGS__>, p, cfg, sb, stream)))
 	switch (cfg.variant)
 	{
-	case 1: return PT_PICK(traceKernel, , 0);
-	case 4: return PT_PICK(traceKernel, , 1);
-	case 5: return PT_PICK(traceKernel, , 2);
-	case 2: return PT_PICK(traceKernelV2, , 8);
-	case 3: return PT_PICK(traceKernelV2, , 24);
-	default: return PT_PICK(traceKernelV2, , 16);
+	case 1: return PT_PICK(traceKernel, , 0);      // per-lane if/else traversal
+	case 4: return PT_PICK(traceKernel, , 1);      // while-while traversal
+	case 2: return PT_PICK(traceKernelV2, , 8);    // stage-voting warp scheduler
+	case 3: return PT_PICK(traceKernelV2, , 16);
+	default: return PT_PICK(traceKernel, , 2);     // while-while + speculative leaf parking (fastest measured)
 	}
 #undef PT_PICK
 }

@@ -1,0 +1,43 @@
+"""Sample-partitioned multi-GPU rendering: one process per GPU, every rank renders every pixel for its
+own share of the GLOBAL sample indices, and the float4 accumulation buffers are combined with ONE sum-reduce
+(torch.distributed: NCCL over NVLink on GPUs, gloo in the CPU tests).  Because the Philox stream is keyed on
+(pixel, global sample index, bounce), the union of the ranks' samples is exactly the single-GPU sample set."""
+import numpy as np
+
+
+def partition_samples(spp, rank, world):
+    """Interleaved partition of the global sample indices 0..spp-1: rank r takes r, r+world, r+2*world, ...
+    Returns (sample_offset, sample_stride, count) - the values of the "sample_offset"/"sample_stride" options and the
+    spp argument of pt_render for that rank."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    count = (spp - rank + world - 1) // world if spp > rank else 0
+    return rank, world, count
+
+
+def render_partitioned(tracer, camera, spp, rank, world, ignore_history=True):
+    """Render this rank's share into the tracer's accumulation buffer.  Returns the number of samples rendered."""
+    off, stride, count = partition_samples(spp, rank, world)
+    tracer.setOption("sample_stride", stride)
+    tracer.setOption("sample_offset", off)
+    tracer.render(camera, count, ignore_history)
+    return count
+
+
+def reduce_accumulation(accum_tensor, dst=0, group=None, all_ranks=False):
+    """The single collective of the path: sum the (H, W, 4) float32 accumulation buffers over ranks."""
+    import torch.distributed as dist
+    if all_ranks:
+        dist.all_reduce(accum_tensor, op=dist.ReduceOp.SUM, group=group)
+    else:
+        dist.reduce(accum_tensor, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return accum_tensor
+
+
+def attach_torch_accumulator(tracer, device):
+    """Allocate the accumulation buffer as a torch tensor (so torch.distributed can reduce it in place) and hand its
+    device pointer to the tracer (pt_set_accum_device_ptr)."""
+    import torch
+    t = torch.zeros((tracer.height, tracer.width, 4), dtype=torch.float32, device=device)
+    tracer.setAccumDevicePtr(t.data_ptr())
+    return t

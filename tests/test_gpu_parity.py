@@ -1,0 +1,322 @@
+"""`-m gpu`: the CUDA path, called through the C ABI (libpt_b200.so), against the oracle, the golden fixtures produced
+by the reference's own GPU code, and size-independent properties at BASELINE.json's full sizes."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import pathtracercuda_b200 as pt
+from pathtracercuda_b200 import scenegen
+from oracle import imgio, orc
+from tests.helpers import GOLDEN, ROOT, bits, golden_objects, load_golden
+
+pytestmark = pytest.mark.gpu
+CLI = os.path.join(ROOT, "pathtracercuda_b200", "bin", "pathtracer_b200")
+EARTH = None
+SKY = None
+
+
+def _assets():
+    global EARTH, SKY
+    if EARTH is None:
+        EARTH, SKY = imgio.read_png(pt.ASSETS + "/earth.png"), imgio.read_hdr(pt.ASSETS + "/skybox.hdr")
+    return EARTH, SKY
+
+
+def _scene(name, W, H):
+    if name.startswith("synthetic_"):
+        objs, cam = scenegen.synthetic_scene(int(name.split("_")[1]), W, H)
+        return objs, cam
+    objs, tex, sky, cam = pt.parse_scene_py(f"{pt.ASSETS}/scenes/{name}.json", W, H)
+    return objs, cam
+
+
+# ---- gate 1: deterministic primary pass - index bit-exact, t within 1e-5 relative ---------------------------------------
+@pytest.mark.parametrize("name", ["cornell_box", "generated_scene", "synthetic_1500"])
+def test_primary_pass_vs_reference_gpu(name):
+    """against the reference's own hitBVH run on a B200 (tests/golden/refgpu_primary_*.npz, tools/make_golden_gpu.py)"""
+    g = load_golden(f"refgpu_primary_{name}")
+    W, H = int(g["W"]), int(g["H"])
+    objs, cam = _scene(name, W, H)
+    with pt.Pathtracer(W, H) as P:
+        P.setScene(objs)
+        idx, t = P.primaryPass(cam)
+    O = orc.Oracle(objs)
+    mism = np.nonzero(idx != g["idx"])[0]
+    for p in mism:  # a mismatch is only acceptable at an exact geometric tie (two objects at the same t, Q7/Q8)
+        ray = O.camera_ray(cam, np.float32((p % W + 0.5) / W), np.float32((p // W + 0.5) / H))
+        a, b = O.hit_object(int(idx[p]), ray[:3], ray[3:]), O.hit_object(int(g["idx"][p]), ray[:3], ray[3:])
+        assert idx[p] >= 0 and g["idx"][p] >= 0 and a is not None and b is not None and abs(a[0] - b[0]) <= 1e-5 * a[0], p
+    assert len(mism) <= 1e-5 * W * H + 4
+    same = (idx == g["idx"]) & (idx >= 0)
+    rel = np.abs(t - g["t"])[same] / g["t"][same]
+    assert rel.max() <= 1e-5, rel.max()
+
+
+@pytest.mark.parametrize("name", ["cornell_box", "generated_scene", "synthetic_1500"])
+def test_primary_and_secondary_vs_oracle(name):
+    """against the CPU oracle (= the reference's host math, pinned bit-exactly).  Host (no FMA) and device (FMA)
+    arithmetic differ in the last bits (the reference GPU build differs from its own host build by up to 2.5e-5 in t),
+    so silhouette pixels may flip: bounded, and everything else close."""
+    d = load_golden(name)
+    objs, cam = golden_objects(d)
+    W, H = int(d["W"]), int(d["H"])
+    with pt.Pathtracer(W, H) as P:
+        P.setScene(objs)
+        idx, t = P.primaryPass(cam)
+        si, st, sn = P.traceRays(d["sec_o"], d["sec_d"])
+    same = idx == d["primary_idx"]
+    assert (~same).mean() < 2e-3
+    h = same & (idx >= 0)
+    rel = np.abs(t - d["primary_t"])[h] / d["primary_t"][h]
+    assert np.quantile(rel, 0.99) < 1e-4 and rel.max() < 0.1  # FMA (device) vs no-FMA (host) rounding; the strict 1e-5 gate is vs the reference GPU above
+    ssame = si == d["sec_idx"]
+    assert ssame.mean() > 0.995
+    h = ssame & (si >= 0)
+    assert np.quantile(np.abs(st - d["sec_t"])[h] / np.maximum(d["sec_t"][h], 1.0), 0.99) < 1e-4  # tiny self-hit distances: absolute error
+    assert np.quantile(np.abs(sn - d["sec_n"])[h].max(-1), 0.99) < 1e-3
+
+
+def test_full_size_primary_properties():
+    """1080p generated_scene: determinism, and agreement of the render path's first segment with the primary pass"""
+    W, H = 1920, 1080
+    objs, cam = _scene("generated_scene", W, H)
+    with pt.Pathtracer(W, H) as P:
+        P.setScene(objs)
+        a = P.primaryPass(cam)
+        b = P.primaryPass(cam)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(bits(a[1]), bits(b[1]))
+        assert 0.55 < (a[0] >= 0).mean() < 0.60  # hit fraction 0.572
+        # emissive-only check: paint every object with its own emission, 1 bounce, black sky -> image == f(index)
+        for i, o in enumerate(objs):
+            o.material.emissive[:] = [float(i + 1), 0.0, 0.0]
+        P.setScene(objs)
+        P.setOption("max_bounces", 1)
+        P.render(cam, 4, True)
+        img = P.getHDRMean()[..., 0].reshape(-1)
+        # pixel-centre and jittered rays agree away from edges: compare on pixels whose 4 neighbours share the index
+        idx2 = a[0].reshape(H, W)
+        inner = np.ones((H, W), bool)
+        for dy, dx in ((0, 1), (1, 0), (0, -1), (-1, 0), (1, 1), (-1, -1), (1, -1), (-1, 1)):
+            inner &= np.roll(idx2, (dy, dx), (0, 1)) == idx2
+        inner[0, :] = inner[-1, :] = inner[:, 0] = inner[:, -1] = False
+        exp = (idx2 + 1).astype(np.float32)
+        assert np.mean(np.abs(img.reshape(H, W)[inner] - exp[inner]) < 1e-3) > 0.999
+
+
+# ---- gate 2: path tracing ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scene,W,H,spp", [("cornell_box", 64, 64, 64), ("generated_scene", 96, 54, 64)])
+def test_render_matches_oracle_path_for_path(scene, W, H, spp):
+    """same Philox stream -> GPU and oracle trace the same paths; bit-level arithmetic differs, a few paths diverge"""
+    earth, sky = _assets()
+    objs, cam = _scene(scene, W, H)
+    O = orc.Oracle(objs)
+    O.add_texture(earth)
+    if scene == "generated_scene":
+        O.set_skybox(O.add_texture(sky))
+    a, ra = O.render(cam, W, H, spp)
+    with pt.Pathtracer(W, H) as P:
+        cam2 = P.loadSceneFile(f"{pt.ASSETS}/scenes/{scene}.json", cwd=pt.ASSETS)
+        assert bytes(cam2) == bytes(cam)
+        P.render(cam2, spp, True)
+        b = P.getHDRMean() * spp
+        st = P.stats()
+    assert abs(int(st.rays) - int(ra)) <= 5e-4 * ra and st.samples == W * H * spp
+    rel = np.abs(a - b)[..., :3] / (np.abs(a[..., :3]) + 1e-3 * spp)
+    assert (rel.max(-1) > 1e-3).mean() < 0.04
+    assert abs(a[..., :3].mean() / b[..., :3].mean() - 1) < 2e-3
+    assert imgio.rmse(a / spp, b / spp)[0] < 0.02
+
+
+@pytest.mark.parametrize("scene", ["cornell_box", "generated_scene"])
+def test_converged_image_within_reference_noise_floor(scene):
+    """north_star gate: RMSE(ours, reference) <= 1.1 x RMSE(reference seed A, reference seed B) at 4096 spp on linear HDR,
+    non-finite pixels masked and counted; the reference images come from the unmodified reference program on a B200."""
+    g = load_golden(f"refpt_{scene}")
+    W, H, spp = int(g["W"]), int(g["H"]), int(g["spp"])
+    A, B = g["A"].astype(np.float32), g["B"].astype(np.float32)
+    with pt.Pathtracer(W, H) as P:
+        cam = P.loadSceneFile(f"{pt.ASSETS}/scenes/{scene}.json", cwd=pt.ASSETS)
+        P.render(cam, spp, True)
+        img = P.getHDRMean()[..., :3]
+        st = P.stats()
+    floor, nfA = imgio.rmse(A, B)
+    ours_a, nf1 = imgio.rmse(img, A)
+    ours_b, nf2 = imgio.rmse(img, B)
+    assert nf1 <= nfA + 8 and nf2 <= nfA + 8
+    assert ours_a <= 1.1 * floor and ours_b <= 1.1 * floor, (ours_a, ours_b, floor)
+    assert abs(st.rays / st.samples / float(g["rays_per_sample"]) - 1) < 5e-3
+    fin = np.isfinite(A).all(-1)
+    assert abs(img[fin].mean() / A[fin].mean() - 1) < 5e-3
+
+
+def test_kernel_variants_bit_identical():
+    """every scheduling variant of the trace kernel computes the same image bit for bit (counter-based RNG + per-pixel
+    in-order accumulation make the result independent of which lane traces which path when)"""
+    imgs = {}
+    for v in (1, 4, 2, 0):
+        with pt.Pathtracer(320, 180) as P:
+            cam = P.loadSceneFile(f"{pt.ASSETS}/scenes/generated_scene.json", cwd=pt.ASSETS)
+            P.setOption("variant", v)
+            P.render(cam, 16, True)
+            P.render(cam, 16, False)
+            imgs[v] = P.getHDRMean()
+    for v in imgs:
+        assert np.array_equal(bits(imgs[1]), bits(imgs[v])), v
+    with pt.Pathtracer(320, 180) as P:  # shared-memory scene vs global-memory scene
+        cam = P.loadSceneFile(f"{pt.ASSETS}/scenes/generated_scene.json", cwd=pt.ASSETS)
+        P.setOption("smem_scene", 0)
+        P.render(cam, 32, True)
+        assert P.stats().scene_in_smem == 0
+        # a different template instantiation: nvcc may contract multiply-adds differently, so last-bit differences
+        assert np.allclose(P.getHDRMean(), imgs[1], rtol=1e-4, atol=1e-5)
+
+
+def test_accumulation_semantics_and_q1_normalisation():
+    W, H = 128, 72
+    with pt.Pathtracer(W, H) as P:
+        cam = P.loadSceneFile(f"{pt.ASSETS}/scenes/cornell_box.json", cwd=pt.ASSETS)
+        P.render(cam, 24, True)
+        one = P.getHDRMean()
+        ref_norm = P.getHDRImageData()
+        assert np.allclose(ref_norm, one * 24, rtol=1e-6)  # reference: sum / number of render() calls (Q1) = sum / 1
+        assert np.all(ref_norm[..., 3] == 1.0)
+        P.render(cam, 8, True)
+        for _ in range(2):
+            P.render(cam, 8, False)
+        three = P.getHDRMean()
+        assert np.allclose(three, one, rtol=2e-5, atol=1e-6)  # 3 x 8 samples continue the same global sample indices
+        assert np.allclose(P.getHDRImageData()[..., :3], three[..., :3] * 8, rtol=1e-6)  # sum / 3 calls
+        assert np.allclose(P.getHDRImageData()[..., 3], 1.0 / 3.0)  # alpha: kernel writes 1, host scales all four channels
+        # the CLI's compat switch: one launch of 24 samples counted as ceil(24/8) = 3 reference calls
+        P.setOption("frames_per_spp", 8)
+        P.render(cam, 24, True)
+        assert np.allclose(P.getHDRImageData()[..., :3], one[..., :3] * 8, rtol=1e-6)
+        # tonemap (kernels/tonemap.cu) against the oracle's restatement on the same accumulation
+        ldr = P.getImageData()
+        O = orc.Oracle([pt.make_object("SPHERE")])
+        exp = O.tonemap(P.getHDRMean() * 24, 3)
+        assert (np.abs(ldr.astype(int) - exp.astype(int)) <= 1).all() and (ldr != exp).mean() < 0.01
+        assert np.all(ldr[..., 3] == 255)
+        # spp == 0 and the sample partition options
+        P.setOption("frames_per_spp", 0)
+        P.render(cam, 0, False)
+        P.setOption("sample_stride", 2)
+        P.setOption("sample_offset", 0)
+        P.render(cam, 12, True)
+        even = P.getHDRMean() * 12
+        P.setOption("sample_offset", 1)
+        P.render(cam, 12, True)
+        odd = P.getHDRMean() * 12
+        assert np.allclose((even + odd)[..., :3], one[..., :3] * 24, rtol=2e-5, atol=1e-5)
+
+
+def test_edge_cases():
+    with pt.Pathtracer(33, 17) as P:  # odd size, no scene: render is a no-op on a zeroed buffer
+        cam = pt.make_camera((0, 0, 3), (0, 0, 0), 60, 33 / 17)
+        P.setScene([])
+        P.render(cam, 4, True)
+        assert not P.getHDRImageData().any()
+        idx, t = P.primaryPass(cam)
+        assert (idx == -1).all()
+        # a single object (root with an empty child), every shape, camera inside a cube (Q2)
+        for shape in pt.SHAPES:
+            P.setScene([pt.make_object(shape, rotation_deg=(30, 20, 10), emissive=(1, 1, 1))])
+            P.setOption("max_bounces", 1)
+            P.render(cam, 8, True)
+            img = P.getHDRMean()
+            assert np.isfinite(img).all() and img[..., :3].max() == 1.0
+        P.setScene([pt.make_object("CUBE", scale=(10, 10, 10), emissive=(2, 2, 2))])
+        idx, t = P.primaryPass(cam)
+        assert (idx == 0).all() and (t == np.float32(0.001)).all()
+        assert P.loadTexture("/nonexistent.png") == 0
+        hs = [P.loadTextureMem(np.full((2, 2, 4), 128, np.uint8)) for _ in range(66)]
+        assert hs[:64] == list(range(1, 65)) and hs[64:] == [0, 0]  # MAX_TEXTURE_COUNT 64
+    with pytest.raises(pt.PtError):
+        pt.Pathtracer(0, 10)
+
+
+def test_textures_and_skybox():
+    earth, sky = _assets()
+    W, H = 96, 96
+    objs = [pt.make_object("SPHERE", material="LAMBERT", texture=1), pt.make_object("QUAD", position=(0, -1, 0), scale=(3, 1, 3), texture=1),
+            pt.make_object("CYLINDER", position=(2, 0, 0), scale=(0.5, 1, 0.5), texture=1), pt.make_object("DISK", position=(-2, 0, 0), rotation_deg=(90, 0, 0), texture=1)]
+    cam = pt.make_camera((0, 1.5, 5), (0, 0, 0), 55, 1.0)
+    O = orc.Oracle(objs)
+    assert O.add_texture(earth) == 1
+    O.set_skybox(O.add_texture(sky))
+    a, _ = O.render(cam, W, H, 32)
+    with pt.Pathtracer(W, H) as P:
+        assert P.loadTexture(pt.ASSETS + "/earth.png") == 1 and P.loadTexture(pt.ASSETS + "/skybox.hdr") == 2
+        P.setSkyboxTextureHandle(2)
+        P.setScene(objs)
+        P.render(cam, 32, True)
+        b = P.getHDRMean() * 32
+    rel = np.abs(a - b)[..., :3] / (np.abs(a[..., :3]) + 0.05)
+    assert (rel.max(-1) > 2e-3).mean() < 0.03 and abs(a[..., :3].mean() / b[..., :3].mean() - 1) < 2e-3
+
+
+def test_cli_end_to_end(tmp_path):
+    """the drop-in surface: same flags, same stdout lines, PNG / HDR files that decode to the API's images"""
+    W, H, spp = 160, 90, 24
+    png, hdr = str(tmp_path / "o.png"), str(tmp_path / "o.hdr")
+    r = subprocess.run([CLI, "-w", str(W), "-h", str(H), "-spp", str(spp), "-o", png, "scenes/generated_scene.json"], cwd=pt.ASSETS, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.splitlines()
+    assert lines[:9] == ["Beginning rendering in configuration:", f"Width: {W}", f"Height: {H}", f"Samples per Pixel: {spp}", "Window: 0", "Controls: 0",
+                         "Output HDR: 0", f"Output Filepath: {png}", "Input Filepath: scenes/generated_scene.json"]
+    assert "Accumulated 0 samples" in lines and any(l.startswith(f"Finished accumulating {spp} samples in ") and l.endswith(" ms GPU time") for l in lines)
+    assert lines[-1] == f"Writing result to {png}"
+    r = subprocess.run([CLI, "-w", str(W), "-h", str(H), "-spp", str(spp), "-ohdr", "-o", hdr, "scenes/generated_scene.json"], cwd=pt.ASSETS, capture_output=True, text=True)
+    assert r.returncode == 0 and "Output HDR: 1" in r.stdout
+    with pt.Pathtracer(W, H) as P:
+        cam = P.loadSceneFile(f"{pt.ASSETS}/scenes/generated_scene.json", cwd=pt.ASSETS)
+        P.setOption("frames_per_spp", 8)
+        P.render(cam, spp, True)
+        ldr, hd = P.getImageData(), P.getHDRImageData()
+    assert np.array_equal(imgio.read_png(png)[::-1], ldr)
+    back = imgio.read_hdr(hdr)[::-1, :, :3]
+    assert (np.abs(back - hd[..., :3]) <= hd[..., :3].max(-1, keepdims=True) / 128 + 1e-6).all()  # RGBE: 8 bits, shared exponent of the max channel
+    r = subprocess.run([CLI, "missing.json"], cwd=pt.ASSETS, capture_output=True, text=True)
+    assert r.returncode == 1 and "Failed to open input file: missing.json" in r.stdout
+
+
+def test_reference_program_agrees(tmp_path):
+    """the unmodified reference program (oracle/_ref/ref_pt) and ours on the same scene, same box: means within noise"""
+    if not os.path.exists(orc.REF_PT):
+        pytest.skip("oracle/_ref/ref_pt not built")
+    W, H, spp = 192, 108, 512
+    out = str(tmp_path / "ref.hdr")
+    r = subprocess.run([orc.REF_PT, "-w", str(W), "-h", str(H), "-spp", str(spp), "-ohdr", "-o", out, "scenes/generated_scene.json"], cwd=pt.ASSETS, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ref = imgio.read_hdr(out)[::-1, :, :3]
+    with pt.Pathtracer(W, H) as P:
+        cam = P.loadSceneFile(f"{pt.ASSETS}/scenes/generated_scene.json", cwd=pt.ASSETS)
+        P.setOption("frames_per_spp", 8)
+        P.render(cam, spp, True)
+        ours = P.getHDRImageData()[..., :3]
+    fin = np.isfinite(ref).all(-1) & np.isfinite(ours).all(-1)
+    assert abs(ours[fin].mean() / ref[fin].mean() - 1) < 0.01
+    assert imgio.rmse(ours, ref)[0] < 0.5 * ref[fin].mean()
+
+
+def test_large_synthetic_scene_global_memory_path():
+    """10k objects: the scene no longer fits in shared memory; the kernel reads it through the read-only path"""
+    W, H = 320, 180
+    objs, cam = scenegen.synthetic_scene(10000, W, H)
+    O = orc.Oracle(objs)
+    io, to, _ = O.primary_pass(cam, W, H)
+    with pt.Pathtracer(W, H) as P:
+        P.setScene(objs)
+        idx, t = P.primaryPass(cam)
+        P.render(cam, 8, True)
+        st = P.stats()
+        img = P.getHDRMean()
+    assert st.scene_in_smem == 0 and st.bvh_nodes >= 5000
+    assert (idx != io).mean() < 2e-3
+    a, ra = O.render(cam, W, H, 8)
+    # the host oracle (no FMA) re-hits curved surfaces slightly more often than any GPU build does: on quadric-only
+    # scenes the reference's own GPU code traces 0.1-0.7 % fewer rays than its host build (measured) and so do we
+    assert -1e-2 * ra < int(st.rays) - int(ra) < 2e-3 * ra
+    assert np.isfinite(img).all()

@@ -1,0 +1,203 @@
+"""Host-side logic of the product library that needs no GPU: the JSON scene loader, the image codecs, the scene
+compiler's BVH, the C-ABI surface and the CLI's argument handling."""
+import ctypes as C
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import pathtracercuda_b200 as pt
+from pathtracercuda_b200 import api, scenegen
+from oracle import imgio, orc
+from tests.emu.emu import Emu
+from tests.helpers import ROOT, bits, golden_objects, load_golden
+
+CLI = os.path.join(ROOT, "pathtracercuda_b200", "bin", "pathtracer_b200")
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "pt_b200.h")).read()
+    declared = set(re.findall(r"\b(pt_[a-z_0-9]+)\s*\(", hdr))
+    assert declared == set(api.EXPORTS), declared ^ set(api.EXPORTS)
+    L = pt.load_library()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert b"sm_100a" in L.pt_version()
+    assert C.sizeof(pt.ObjectDesc) == 80 and C.sizeof(pt.CameraDesc) == 44 and C.sizeof(pt.MaterialDesc) == 40
+
+
+@pytest.mark.skipif(__import__("tests.conftest", fromlist=["HAS_GPU"]).HAS_GPU, reason="box has a GPU")
+def test_no_cpu_fallback():
+    with pytest.raises(pt.PtError, match="no CUDA device"):
+        pt.Pathtracer(16, 16)
+
+
+@pytest.mark.parametrize("scene", ["cornell_box", "generated_scene"])
+def test_scene_loader_matches_schema_mirror_and_reference(scene):
+    path = f"{pt.ASSETS}/scenes/{scene}.json"
+    objs, paths, sky, cam = pt.parse_scene_file(path, 1920, 1080)
+    o2, p2, s2, c2 = pt.parse_scene_py(path, 1920, 1080)
+    assert paths == p2 and sky == s2 and bytes(cam) == bytes(c2)
+    assert len(objs) == len(o2) and all(bytes(a) == bytes(b) for a, b in zip(objs, o2))
+    # and against the objects the REFERENCE's own loader produced (golden fixture, via libref_host)
+    g, gcam = golden_objects(load_golden(scene))
+    assert all(bytes(a) == bytes(b) for a, b in zip(objs, g))
+
+
+def test_scene_loader_quirks(tmp_path):
+    scene = {"camera": {"position": [1, 2, 3], "fovy": 40}, "skybox": "",
+             "objects": [{"type": "TORUS", "rotation": [90, 0, 0], "material": {"type": "GLASS", "roughness": 1, "metalness": 0.25, "texture": "a.png"}},
+                         {"type": "DISK", "scale": [2.0, 3.0, 4.0], "material": {"texture": "a.png", "emissive": [1, 2, 3]}}, {}]}
+    p = tmp_path / "s.json"
+    p.write_text(json.dumps(scene))
+    objs, paths, sky, cam = pt.parse_scene_file(str(p), 200, 100)
+    assert len(objs) == 3 and paths == ["a.png"] and sky == 0
+    assert objs[0].type == pt.SHAPES["SPHERE"] and objs[0].material.type == pt.MATERIALS["LAMBERT"]  # unknown names keep defaults
+    assert objs[0].material.roughness == 0.5  # integer literal ignored (Q5) ...
+    assert objs[0].material.metalness == 0.25  # ... float literal read
+    assert abs(objs[0].rotation[0] - np.float32(np.pi / 2)) < 1e-6
+    assert objs[0].material.texture == 1 and objs[1].material.texture == 1  # de-duplicated by path
+    assert list(objs[1].material.emissive) == [1.0, 2.0, 3.0] and list(objs[1].scale) == [2.0, 3.0, 4.0]
+    assert objs[2].type == 0 and list(objs[2].scale) == [1.0, 1.0, 1.0]
+    assert list(cam.position) == [1.0, 2.0, 3.0] and list(cam.look_at) == [0.0, 0.0, -1.0]
+    assert abs(cam.fovy - np.float32(np.pi / 3)) < 1e-6 and cam.aspect == 2.0  # "fovy": 40 is an int literal -> default 60
+    for bad in ["{", '{"objects": [1,]}', '{"a": 01}', "[1] x"]:
+        p.write_text(bad)
+        with pytest.raises(pt.PtError, match="JSON parse error"):
+            pt.parse_scene_file(str(p), 4, 4)
+    with pytest.raises(pt.PtError, match="Failed to open input file"):
+        pt.parse_scene_file(str(tmp_path / "missing.json"), 4, 4)
+    p.write_text('{"objects": [{"position": ["x", 0, 0]}]}')
+    with pytest.raises(pt.PtError, match="type must be number"):
+        pt.parse_scene_file(str(p), 4, 4)
+    p.write_text('﻿{"skybox": "sky\\u0041.hdr", "objects": []}')
+    objs, paths, sky, cam = pt.parse_scene_file(str(p), 4, 4)
+    assert objs == [] and paths == ["skyA.hdr"] and sky == 1
+
+
+def test_image_codecs(tmp_path):
+    # decoders vs independent ones (PIL / numpy)
+    assert np.array_equal(pt.read_image(pt.ASSETS + "/earth.png"), imgio.read_png(pt.ASSETS + "/earth.png"))
+    assert np.array_equal(bits(pt.read_image(pt.ASSETS + "/skybox.hdr")), bits(imgio.read_hdr(pt.ASSETS + "/skybox.hdr")))
+    rng = np.random.default_rng(3)
+    from PIL import Image
+    for mode, arr in {"L": rng.integers(0, 256, (7, 5), np.uint8), "LA": rng.integers(0, 256, (7, 5, 2), np.uint8),
+                      "RGB": rng.integers(0, 256, (9, 13, 3), np.uint8), "RGBA": rng.integers(0, 256, (9, 13, 4), np.uint8)}.items():
+        f = str(tmp_path / f"{mode}.png")
+        Image.fromarray(arr, mode).save(f)
+        assert np.array_equal(pt.read_image(f), imgio.read_png(f)), mode
+    pal = Image.fromarray(rng.integers(0, 256, (8, 8, 3), np.uint8), "RGB").quantize(16)
+    pal.save(str(tmp_path / "pal.png"))
+    assert np.array_equal(pt.read_image(str(tmp_path / "pal.png")), imgio.read_png(str(tmp_path / "pal.png")))
+    (tmp_path / "bad.png").write_bytes(b"not a png")
+    with pytest.raises(pt.PtError):
+        pt.read_image(str(tmp_path / "bad.png"))
+    # writers: flip on write (buffer row 0 = bottom of the view), PNG lossless, HDR = stb's truncating RGBE
+    img8 = rng.integers(0, 256, (11, 17, 4), np.uint8)
+    img8[..., 3] = 255
+    f = str(tmp_path / "o.png")
+    pt.write_png(f, img8)
+    assert np.array_equal(imgio.read_png(f), img8[::-1])
+    for w in (5, 40):  # flat (w < 8) and run-length encoded scanlines
+        imgf = (rng.random((6, w, 4)).astype(np.float32) ** 4) * 50
+        imgf[1, :, :] = 0.25  # long runs
+        imgf[2, 0] = 0
+        f = str(tmp_path / f"o{w}.hdr")
+        pt.write_hdr(f, imgf)
+        back = imgio.read_hdr(f)[::-1]
+        m = imgf[..., :3].max(-1)
+        e = np.frexp(m)[1]
+        expect = np.floor(imgf[..., :3] * (np.frexp(m)[0] * 256.0 / np.maximum(m, 1e-38))[..., None]) * np.ldexp(1.0, e - 8)[..., None]
+        expect[m < 1e-32] = 0
+        assert np.allclose(back[..., :3], expect, rtol=1e-6, atol=0)
+        assert np.array_equal(bits(pt.read_image(f)), bits(imgio.read_hdr(f)))  # our reader on our writer
+        assert open(f, "rb").read().startswith(b"#?RADIANCE\n# Written by stb_image_write.h\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=          1.0000000000000\n\n-Y 6 +X ")
+
+
+def _validate_bvh(objs, max_leaf=4):
+    E = Emu(objs, max_leaf)
+    nodes, prims = E.arrays()
+    O = orc.Oracle(objs)
+    boxes = np.array([O.object_info(i)[1] for i in range(len(objs))])
+    nf = nodes.view(np.float32)
+    seen = np.zeros(len(objs), int)
+    assert sorted(prims[:, 13].tolist()) == list(range(len(objs)))  # sceneIndex is a permutation
+
+    def walk(ref, depth):
+        if ref < 0:
+            u = ref & 0xffffffff
+            first, count, typ = u & 0xffffff, (u >> 24) & 15, (u >> 28) & 7
+            assert 1 <= count <= max(max_leaf, 1)
+            assert typ == prims[first, 12]
+            b = np.array([[np.inf] * 3, [-np.inf] * 3])
+            for k in range(first, first + count):
+                s = prims[k, 13]
+                seen[s] += 1
+                b[0] = np.minimum(b[0], boxes[s][:3])
+                b[1] = np.maximum(b[1], boxes[s][3:])
+            return b, depth
+        n = nf[ref]
+        kids = nodes[ref, 12:14].view(np.int32)
+        out = np.array([[np.inf] * 3, [-np.inf] * 3])
+        dmax = depth
+        for c in range(2):
+            if kids[c] == -2 ** 31:
+                continue
+            b, d = walk(int(kids[c]), depth + 1)
+            stored = np.array([n[6 * c:6 * c + 3], n[6 * c + 3:6 * c + 6]])
+            assert (stored[0] <= b[0]).all() and (stored[1] >= b[1]).all(), "child box must contain its primitives"
+            out[0] = np.minimum(out[0], stored[0])
+            out[1] = np.maximum(out[1], stored[1])
+            dmax = max(dmax, d)
+        return out, dmax
+
+    _, depth = walk(0, 0)
+    assert (seen == 1).all(), "every primitive in exactly one leaf (reference BVH::validate)"
+    info = E.info()
+    assert info[0] == len(nodes) and depth <= info[1] + 1
+    return info
+
+
+def test_bvh_structure():
+    for name in ("cornell_box", "generated_scene"):
+        objs, _ = golden_objects(load_golden(name))
+        _validate_bvh(objs)
+    objs, _ = scenegen.synthetic_scene(3000, 64, 36)
+    nodes, depth, leaves = _validate_bvh(objs)
+    assert depth < 40
+    _validate_bvh([pt.make_object("SPHERE")])                        # a single object: root with one empty child
+    _validate_bvh([pt.make_object("CUBE")] * 9, max_leaf=2)          # coincident centroids: median fallback
+    _validate_bvh([pt.make_object("QUAD", position=(i, 0, 0)) for i in range(5)], max_leaf=8)
+
+
+def test_cli_arguments():
+    assert os.path.exists(CLI), "build the CLI with make -C pathtracercuda_b200/csrc"
+    # like the reference, options are only parsed in argv[1..argc-2]; the last argument is always the scene path
+    # (main.cpp:40,146-149), so a lone "-help" is taken as the input file and help needs a second argument
+    r = subprocess.run([CLI, "-help", "x.json"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("USAGE: PathtracerCUDA.exe [options] <input file>")
+    for opt in ("-help", "-w", "-h", "-spp", "-window", "-enable_controls", "-o", "-ohdr"):
+        assert re.search(rf"^{opt}\s", r.stdout, re.M), opt
+    r = subprocess.run([CLI], capture_output=True, text=True)
+    assert r.returncode == 0 and "Missing input file argument!" in r.stdout
+    r = subprocess.run([CLI, "-w", "0", "x.json"], capture_output=True, text=True)
+    assert r.returncode == 0 and "Invalid input for -w!" in r.stdout
+    r = subprocess.run([CLI, "-bogus", "x.json"], capture_output=True, text=True)
+    assert r.returncode == 0 and "Can't parse argument: -bogus" in r.stdout
+
+
+def test_synthetic_generator_deterministic(tmp_path):
+    a = scenegen.synthetic_scene_dict(200)
+    b = scenegen.synthetic_scene_dict(200)
+    assert a == b and len(a["objects"]) == 201
+    kinds = {o["type"] for o in a["objects"]}
+    mats = {o["material"]["type"] for o in a["objects"]}
+    assert kinds == set(pt.SHAPES) and mats == set(pt.MATERIALS)
+    f = tmp_path / "syn.json"
+    scenegen.write_synthetic_scene(str(f), 200)
+    objs, paths, sky, cam = pt.parse_scene_file(str(f), 64, 36)
+    o2, c2 = scenegen.synthetic_scene(200, 64, 36)
+    assert all(bytes(x) == bytes(y) for x, y in zip(objs, o2))
