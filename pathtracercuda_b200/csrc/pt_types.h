@@ -9,12 +9,15 @@ namespace ptb
 
 // One BVH node = the boxes of BOTH children + their references (64 B, one 128-bit x4 fetch tests two boxes).
 // Replaces the reference's 32 B single-box node (BVH.h:6-11), whose traversal needs one dependent fetch per box.
-//   f[0..5]  = child0 min.xyz, max.xyz      f[6..11] = child1 min.xyz, max.xyz
+//   f[0..2] = child0 box CENTRE, f[3..5] = child0 HALF EXTENT (padded outwards by a few ulp of the scene scale),
+//   f[6..8] / f[9..11] = the same for child1.  Centre/half-extent form turns the per-axis min/max pair of the slab test
+//   into FMAs: t_c = c*inv - o*inv, near = t_c - h*|inv|, far = t_c + h*|inv| (9 FMA + 4 min/max per box instead of
+//   6 FMA + 10 min/max: min/max issue at half rate on the ALU pipe, which is what bounded the node loop).
 //   child[k] >= 0 : index of an interior node
 //   child[k] <  0 : leaf; bits 0..23 = first primitive (BVH order), bits 24..27 = primitive count (1..15),
 //                   bits 28..30 = shape type of the first primitive (lets the scheduler bin the next intersection
 //                   by shape class without touching memory)
-//   an EMPTY child has child = kEmptyChild and a degenerate box at +FLT_MAX (never hit)
+//   an EMPTY child has child = kEmptyChild, centre +FLT_MAX and half extent -1 (near > far for every ray: never hit)
 struct alignas(16) Node
 {
 	float f[12];

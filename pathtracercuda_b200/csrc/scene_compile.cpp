@@ -309,6 +309,7 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 		// the empty child's box is a point at +FLT_MAX: its slab interval is degenerate (near == far) for every ray, so the
 		// strict near < far test never passes.  (An inverted box would NOT work: the min/max slab test un-inverts it.)
 		for (int k = 0; k < 3; ++k) { nd.f[k] = rootBox.mn[k]; nd.f[3 + k] = rootBox.mx[k]; nd.f[6 + k] = FLT_MAX; nd.f[9 + k] = FLT_MAX; }
+		// (converted below to centre +FLT_MAX / half extent -1)
 		nd.child[0] = root;
 		nd.child[1] = kEmptyChild;
 		b.nextNode = 1;
@@ -320,6 +321,31 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 		return false;
 	}
 	out.nodes.resize(b.nextNode.load());
+	// min/max -> centre / half extent, padded outwards: the traversal computes t_c = c*inv - o*inv in fp32, so the box
+	// must absorb a few ulp of |c|, of its own size and of the scene scale (ray origins) to stay conservative
+	{
+		float scale = 0.0f;
+		for (int k = 0; k < 3; ++k) scale = std::max(scale, std::max(fabsf(rootBox.mn[k]), fabsf(rootBox.mx[k])));
+		for (Node &nd : out.nodes)
+			for (int c = 0; c < 2; ++c)
+			{
+				float *f = nd.f + 6 * c;
+				if (nd.child[c] == kEmptyChild)
+				{
+					for (int k = 0; k < 3; ++k) { f[k] = FLT_MAX; f[3 + k] = -1.0f; }
+					continue;
+				}
+				for (int k = 0; k < 3; ++k)
+				{
+					const double mn = f[k], mx = f[3 + k];
+					const float ctr = float(0.5 * (mn + mx));
+					double h = std::max(mx - double(ctr), double(ctr) - mn); // covers the rounding of the centre
+					h += 4.0e-7 * (fabs(double(ctr)) + h + double(scale)) + 1e-30;
+					f[k] = ctr;
+					f[3 + k] = nextafterf(float(h), FLT_MAX);
+				}
+			}
+	}
 	out.depth = depth;
 	out.leafCount = b.leafCount.load();
 	for (int k = 0; k < 3; ++k) { out.sceneMin[k] = rootBox.mn[k]; out.sceneMax[k] = rootBox.mx[k]; }

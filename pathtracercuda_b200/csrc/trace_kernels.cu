@@ -267,7 +267,8 @@ __global__ void __launch_bounds__(kThreads, 3) traceKernelV2(const RenderParams 
 	V3 color = mk(0.0f, 0.0f, 0.0f);
 	V3 ro = camO, rd = mk(0.0f, 0.0f, 1.0f), thr = mk(1.0f, 1.0f, 1.0f), L = mk(0.0f, 0.0f, 0.0f);
 	// traversal state
-	float idx = 0.0f, idy = 0.0f, idz = 0.0f, oix = 0.0f, oiy = 0.0f, oiz = 0.0f, tBest = FLT_MAX;
+	TravRay tr = makeTravRay(ro, rd);
+	float tBest = FLT_MAX;
 	int primBest = -1, cur = 0, sp = 0;
 	uint32_t sceneBest = 0, leafPrim = 0, leafLeft = 0;
 	int stack[kStackSize];
@@ -294,10 +295,7 @@ __global__ void __launch_bounds__(kThreads, 3) traceKernelV2(const RenderParams 
 	auto pop = [&]() -> int { return sp > 0 ? stack[--sp] : kSentinel; };
 	auto startRay = [&]()
 	{
-		idx = 1.0f / (rd.x != 0.0f ? rd.x : 1e-7f);
-		idy = 1.0f / (rd.y != 0.0f ? rd.y : 1e-7f);
-		idz = 1.0f / (rd.z != 0.0f ? rd.z : 1e-7f);
-		oix = ro.x * idx; oiy = ro.y * idy; oiz = ro.z * idz;
+		tr = makeTravRay(ro, rd);
 		sp = 0; tBest = FLT_MAX; primBest = -1; sceneBest = 0; cur = 0;
 		want = W_NODE;
 		++rays;
@@ -355,17 +353,9 @@ __global__ void __launch_bounds__(kThreads, 3) traceKernelV2(const RenderParams 
 					const float4 *n = sv.nodes + cur * 4;
 					const float4 A = sv.ld(n), Bq = sv.ld(n + 1), C = sv.ld(n + 2);
 					const float4 Dq = sv.ld(n + 3);
-					const float a0x = __fmaf_rn(A.x, idx, -oix), a1x = __fmaf_rn(A.w, idx, -oix);
-					const float a0y = __fmaf_rn(A.y, idy, -oiy), a1y = __fmaf_rn(Bq.x, idy, -oiy);
-					const float a0z = __fmaf_rn(A.z, idz, -oiz), a1z = __fmaf_rn(Bq.y, idz, -oiz);
-					const float b0x = __fmaf_rn(Bq.z, idx, -oix), b1x = __fmaf_rn(C.y, idx, -oix);
-					const float b0y = __fmaf_rn(Bq.w, idy, -oiy), b1y = __fmaf_rn(C.z, idy, -oiy);
-					const float b0z = __fmaf_rn(C.x, idz, -oiz), b1z = __fmaf_rn(C.w, idz, -oiz);
-					const float nearA = fmaxf(fmaxf(fminf(a0x, a1x), fminf(a0y, a1y)), fmaxf(fminf(a0z, a1z), tMin));
-					const float farA = fminf(fminf(fmaxf(a0x, a1x), fmaxf(a0y, a1y)), fminf(fmaxf(a0z, a1z), tBest));
-					const float nearB = fmaxf(fmaxf(fminf(b0x, b1x), fminf(b0y, b1y)), fmaxf(fminf(b0z, b1z), tMin));
-					const float farB = fminf(fminf(fmaxf(b0x, b1x), fmaxf(b0y, b1y)), fminf(fmaxf(b0z, b1z), tBest));
-					const bool hitA = nearA < farA, hitB = nearB < farB;
+					bool hitA, hitB;
+					float nearA, nearB;
+					testNodeBoxes(A, Bq, C, tr, tMin, tBest, hitA, hitB, nearA, nearB);
 					const int cA = __float_as_int(Dq.x), cB = __float_as_int(Dq.y);
 					int next;
 					if (hitA && hitB)

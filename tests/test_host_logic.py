@@ -147,10 +147,12 @@ def _validate_bvh(objs, max_leaf=4):
             if kids[c] == -2 ** 31:
                 continue
             b, d = walk(int(kids[c]), depth + 1)
-            stored = np.array([n[6 * c:6 * c + 3], n[6 * c + 3:6 * c + 6]])
+            ctr, half = n[6 * c:6 * c + 3].astype(np.float64), n[6 * c + 3:6 * c + 6].astype(np.float64)
+            stored = np.array([ctr - half, ctr + half])      # nodes hold centre / (padded) half extent
+            assert (half < (b[1] - b[0]) * 0.5 * (1 + 1e-5) + 1e-4).all(), "padding must stay tiny"
             assert (stored[0] <= b[0]).all() and (stored[1] >= b[1]).all(), "child box must contain its primitives"
-            out[0] = np.minimum(out[0], stored[0])
-            out[1] = np.maximum(out[1], stored[1])
+            out[0] = np.minimum(out[0], b[0])                # exact bounds of the subtree (the padding is per box, not nested)
+            out[1] = np.maximum(out[1], b[1])
             dmax = max(dmax, d)
         return out, dmax
 
