@@ -41,7 +41,7 @@ struct pt_context
 	// scene
 	float4 *sceneBlob = nullptr;
 	Mat *mats = nullptr;
-	uint32_t nodeCount = 0, primCount = 0, bvhDepth = 0;
+	uint32_t nodeCount = 0, primCount = 0, bvhDepth = 0, globalCount = 0, maxGlobal = ptb::kMaxGlobalPrims;
 	// textures
 	std::vector<void *> texMem;
 	TexDesc texHost[kMaxTextures];
@@ -152,7 +152,7 @@ int pt_set_scene(pt_context *c, size_t count, const pt_object_desc *objects)
 	if (!objects) return setError(PT_E_INVALID, "pt_set_scene: null objects");
 	CompiledScene cs;
 	std::string err;
-	if (!compileScene(count, objects, c->maxLeaf, cs, err)) return setError(PT_E_LIMIT, "pt_set_scene: " + err);
+	if (!compileScene(count, objects, c->maxLeaf, cs, err, c->maxGlobal)) return setError(PT_E_LIMIT, "pt_set_scene: " + err);
 	CK(cudaSetDevice(c->device));
 	CK(cudaStreamSynchronize(c->stream));
 	if (c->sceneBlob) { CK(cudaFree(c->sceneBlob)); c->sceneBlob = nullptr; }
@@ -166,6 +166,7 @@ int pt_set_scene(pt_context *c, size_t count, const pt_object_desc *objects)
 	CK(cudaStreamSynchronize(c->stream));
 	c->nodeCount = uint32_t(cs.nodes.size());
 	c->primCount = uint32_t(cs.prims.size());
+	c->globalCount = cs.globalCount;
 	c->bvhDepth = cs.depth;
 	c->stats.bvh_nodes = c->nodeCount;
 	c->stats.bvh_depth = c->bvhDepth;
@@ -227,6 +228,7 @@ static SceneDev sceneDev(const pt_context *c)
 	s.textures = c->texDev;
 	s.nodeCount = c->nodeCount;
 	s.primCount = c->primCount;
+	s.globalCount = c->globalCount;
 	s.texCount = c->textureCount;
 	s.skybox = (c->skybox <= c->textureCount) ? c->skybox : 0;
 	return s;
@@ -349,6 +351,9 @@ int pt_set_option(pt_context *c, const char *key, double value)
 	else if (k == "max_bounces") c->maxBounces = value < 1 ? 1u : uint32_t(value);
 	else if (k == "max_leaf") c->maxLeaf = value < 1 ? 1u : uint32_t(value);
 	else if (k == "variant") c->launch.variant = int(value);
+	else if (k == "max_global") c->maxGlobal = uint32_t(value < 0 ? 0 : value);
+	else if (k == "trace_low") c->launch.traceLow = int(value);
+	else if (k == "pool_warps") c->launch.poolWarps = int(value);
 	else return setError(PT_E_INVALID, "pt_set_option: unknown option " + k);
 	return PT_OK;
 }

@@ -33,6 +33,11 @@ constexpr uint32_t kLeafStartMask = (1u << kLeafCountShift) - 1u;
 constexpr int32_t kEmptyChild = kLeafBit; // leaf with count 0
 constexpr uint32_t kMaxLeafPrims = 15;
 constexpr int kStackSize = 48;
+// Primitives whose box covers a large share of the scene box (a floor, the walls of a room) are kept OUT of the BVH and
+// tested first by every ray: the whole warp runs the same test on the same record (no divergence, broadcast loads), the
+// traversal starts with a tight t_max, and the tree is not polluted by boxes that overlap everything.
+constexpr uint32_t kMaxGlobalPrims = 8;
+constexpr float kGlobalAreaFraction = 0.25f;
 
 // One primitive = world->local 3x4 (the reference's Hittable rows, Hittable.h:22-24) + shape type + indices (64 B).
 // The 40 B material the reference embeds in every 96 B Hittable (Hittable.h:25) lives in its own table: it is

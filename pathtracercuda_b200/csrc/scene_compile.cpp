@@ -119,6 +119,7 @@ namespace
 {
 constexpr int kBins = 16;
 constexpr float kTraversalCost = 1.0f; // cost of one two-box node fetch + test, in units of...
+constexpr float kHoistFraction = 0.5f; // a primitive whose box has >= this share of the node's box area gets its own leaf at once
 constexpr float kPrimCost = 1.5f;      // ...one primitive intersection (quadric tests are dearer than slab tests)
 
 struct Box
@@ -211,7 +212,25 @@ struct Builder
 			}
 		}
 
-		if (n <= maxLeaf && (bestAxis < 0 || bestCost >= kPrimCost * float(n)))
+		// one more candidate: the primitive with the largest box on its own against all the others.  Centroid binning can
+		// never isolate a primitive that spans the node (a floor under hundreds of small objects): it drags its huge box
+		// down every level of the subtree that happens to hold its centroid.
+		size_t isolate = end;
+		if (n >= 3)
+		{
+			size_t big = begin;
+			float bigArea = -1.0f;
+			for (size_t i = begin; i < end; ++i) { const float a = bp[i].box.area(); if (a > bigArea) { bigArea = a; big = i; } }
+			Box rest;
+			rest.reset();
+			for (size_t i = begin; i < end; ++i) if (i != big) rest.grow(bp[i].box);
+			const float cost = kTraversalCost + kPrimCost * (bigArea + float(n - 1) * rest.area()) / parentArea;
+			// the greedy SAH cost (children costed as leaves) cannot see that damage, so a primitive covering most of the
+			// node is hoisted outright
+			if (cost < bestCost || bigArea >= kHoistFraction * parentArea) { bestCost = std::min(bestCost, cost); isolate = big; }
+		}
+
+		if (n <= maxLeaf && ((bestAxis < 0 && isolate == end) || bestCost >= kPrimCost * float(n)))
 		{
 			depth = 0;
 			leafCount++;
@@ -219,7 +238,12 @@ struct Builder
 		}
 
 		size_t mid = begin;
-		if (bestAxis >= 0)
+		if (isolate != end)
+		{
+			std::swap(bp[begin], bp[isolate]);
+			mid = begin + 1;
+		}
+		else if (bestAxis >= 0)
 		{
 			const float ext = cb.mx[bestAxis] - cb.mn[bestAxis];
 			const float k = float(kBins) / ext, lo = cb.mn[bestAxis];
@@ -271,7 +295,7 @@ struct Builder
 };
 } // namespace
 
-bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf, CompiledScene &out, std::string &err)
+bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf, CompiledScene &out, std::string &err, uint32_t maxGlobal)
 {
 	out = CompiledScene();
 	if (count == 0) { err = "empty scene"; return false; }
@@ -293,6 +317,26 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 		bp[i].index = uint32_t(i);
 	}
 
+	// hoist the primitives that span the scene (pt_types.h kMaxGlobalPrims): largest first, at the front of the order
+	Box sceneBox;
+	sceneBox.reset();
+	for (size_t i = 0; i < count; ++i) sceneBox.grow(bp[i].box);
+	size_t nGlobal = 0;
+	{
+		const float need = kGlobalAreaFraction * sceneBox.area();
+		const size_t cap = std::min<size_t>(std::min<uint32_t>(maxGlobal, kMaxGlobalPrims), count - 1); // keep one primitive for the tree
+		while (nGlobal < cap)
+		{
+			size_t big = nGlobal;
+			float bigArea = -1.0f;
+			for (size_t i = nGlobal; i < count; ++i) { const float a = bp[i].box.area(); if (a > bigArea) { bigArea = a; big = i; } }
+			if (!(bigArea >= need) || !(need > 0.0f)) break;
+			std::swap(bp[nGlobal], bp[big]);
+			++nGlobal;
+		}
+	}
+	out.globalCount = uint32_t(nGlobal);
+
 	out.nodes.assign(std::max<size_t>(count, 2) - 1 + 1, Node());
 	Builder b(bp, out.nodes, maxLeaf, objects);
 	Box rootBox;
@@ -300,7 +344,7 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 	int32_t root;
 #pragma omp parallel if (count > 8192)
 #pragma omp single
-	root = b.build(0, count, rootBox, depth);
+	root = b.build(nGlobal, count, rootBox, depth);
 
 	if (root < 0)
 	{
@@ -325,7 +369,7 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 	// must absorb a few ulp of |c|, of its own size and of the scene scale (ray origins) to stay conservative
 	{
 		float scale = 0.0f;
-		for (int k = 0; k < 3; ++k) scale = std::max(scale, std::max(fabsf(rootBox.mn[k]), fabsf(rootBox.mx[k])));
+		for (int k = 0; k < 3; ++k) scale = std::max(scale, std::max(fabsf(sceneBox.mn[k]), fabsf(sceneBox.mx[k])));
 		for (Node &nd : out.nodes)
 			for (int c = 0; c < 2; ++c)
 			{
@@ -348,7 +392,7 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 	}
 	out.depth = depth;
 	out.leafCount = b.leafCount.load();
-	for (int k = 0; k < 3; ++k) { out.sceneMin[k] = rootBox.mn[k]; out.sceneMax[k] = rootBox.mx[k]; }
+	for (int k = 0; k < 3; ++k) { out.sceneMin[k] = sceneBox.mn[k]; out.sceneMax[k] = sceneBox.mx[k]; }
 	if (depth + 2 > uint32_t(kStackSize)) { err = "BVH deeper than the traversal stack"; return false; }
 
 	out.prims.resize(count);

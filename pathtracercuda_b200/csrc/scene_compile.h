@@ -15,6 +15,7 @@ struct CompiledScene
 	std::vector<Mat> mats;   // BVH order (parallel to prims)
 	uint32_t depth = 0;      // interior-node depth (max traversal stack = depth)
 	uint32_t leafCount = 0;
+	uint32_t globalCount = 0; // prims[0..globalCount) are tested by every ray before the traversal and are not in the BVH
 	float sceneMin[3] = { 0, 0, 0 };
 	float sceneMax[3] = { 0, 0, 0 };
 };
@@ -32,7 +33,7 @@ void computeObjectXform(const pt_object_desc &d, ObjectXform &out);
 
 // Build the BVH (binned SAH, kBins bins, centroid bounds, leaf when cheaper) and flatten it.
 // maxLeaf in [1, kMaxLeafPrims].  Returns false and sets err on failure (depth over kStackSize).
-bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf, CompiledScene &out, std::string &err);
+bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf, CompiledScene &out, std::string &err, uint32_t maxGlobal = kMaxGlobalPrims);
 
 // Camera ctor + update() equivalent (reference Camera.inl:4-23,54-62)
 void computeCamera(const pt_camera_desc &c, CameraDev &out);

@@ -17,6 +17,7 @@
 //   * normals, UVs, the tangent frame and the material fetch happen once per path segment at the closest hit, not once
 //     per accepted candidate (Hittable.inl:129-142).
 #include "trace_device.cuh"
+#include <algorithm>
 
 namespace ptb
 {
@@ -72,11 +73,13 @@ __global__ void __launch_bounds__(kThreads, 3) traceKernel(const RenderParams p)
 		stageSceneToSmem(smemScene, p.scene.sceneBlob, (p.scene.nodeCount + p.scene.primCount) * 64u, &mbar);
 		sv.nodes = smemScene;
 		sv.prims = smemScene + size_t(p.scene.nodeCount) * 4;
+		sv.globalCount = p.scene.globalCount;
 	}
 	else
 	{
 		sv.nodes = p.scene.sceneBlob;
 		sv.prims = p.scene.sceneBlob + size_t(p.scene.nodeCount) * 4;
+		sv.globalCount = p.scene.globalCount;
 	}
 
 	const uint32_t lane = threadIdx.x & 31u;
@@ -222,23 +225,30 @@ __global__ void __launch_bounds__(kThreads, 3) traceKernel(const RenderParams p)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// traceKernelV2 — warp-level wavefront.  Same per-path arithmetic as traceKernel (so the image is bit-identical), but
-// the warp no longer lets every lane run its own control flow.  Each lane is a small state machine whose next step is
-// one of six STAGES:
-//     NODE   one two-box BVH node test            PQ / PF / PC   one primitive test of the quadric / flat / cube class
-//     SHADE  surface + material sample at a hit    GEN            env-miss lookup, accumulate, regenerate a camera ray
-// Every iteration the warp ballots what its lanes want, picks ONE stage (the most populated one) and executes it for
-// exactly the lanes that want it; the others keep their state and wait until their stage is picked, by which time
-// more lanes have joined them.  Divergent work is thereby re-converged by stage - the in-register equivalent of the
-// wavefront queues (generate / traverse / intersect-by-shape-class / shade / env-miss / accumulate) with the ballot
-// as the compaction step and no ray state ever leaving the register file.
+// traceKernelWP — the warp-pool wavefront (default).
+//
+// Every warp owns a POOL of K = 64 path slots in shared memory (struct-of-arrays, 21 words per slot: ray, throughput,
+// path radiance, pixel colour, pixel, sample/bounce state, leftover Philox words, hit t / primitive) - twice as many
+// paths as it has lanes.  Three 64-bit masks in registers say which stage each idle slot waits for:
+//     ready  has a ray, waits for BVH-traverse + intersect          (-> hit | gen when the traversal retires)
+//     hit    has a closest hit, waits for shade / sample            (-> ready if the path continues, else gen)
+//     gen    path ended (env miss, absorbed, max depth) or slot is new: env-miss lookup, accumulate, next sample /
+//            next pixel (warp-aggregated atomic), generate the camera ray   (-> ready, or retired when no pixels are left)
+// Each iteration the warp runs ONE stage for up to 32 slots picked from that stage's mask (ballot/popc prefix
+// compaction into a slot list), so shade and generate execute with (nearly) full warps whatever mixture of path
+// depths the pool holds, and lanes whose traversal retires are refilled from `ready` at once: the traversal loop
+// no longer waits for the longest path of the warp.  The ray being traversed lives in registers (lane state survives
+// the shade / generate stages, which work on OTHER slots); everything else stays in the pool.  A slot owns its pixel
+// for all of its samples, added in order, so the image does not depend on scheduling (bit-identical to traceKernel).
 // ---------------------------------------------------------------------------------------------------------------
-enum : uint32_t { W_NODE = 0, W_PQ = 1, W_PF = 2, W_PC = 3, W_SHADE = 4, W_GEN = 5, W_DONE = 6 };
-constexpr int kSentinel = 0x7fffffff;
-__device__ __forceinline__ uint32_t classOfType(uint32_t type) { return (0x3211211u >> (type * 4u)) & 0xfu; }
+constexpr int kPoolSlots = 64;
+constexpr int kPoolThreads = 768;
+enum : int { F_OX = 0, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_TX, F_TY, F_TZ, F_LX, F_LY, F_LZ, F_CX, F_CY, F_CZ, F_PIXEL, F_STATE, F_RZ, F_RW, F_T, F_PRIM, F_LIST, kPoolWords };
+constexpr uint32_t kStateSampleMask = 0x00ffffffu, kStateBounceShift = 24, kStateHasPath = 0x80000000u;
+constexpr size_t kPoolBytesPerWarp = size_t(kPoolWords) * kPoolSlots * 4;
 
-template <bool SMEM, bool COUNT, int NODE_STICK>
-__global__ void __launch_bounds__(kThreads, 3) traceKernelV2(const RenderParams p)
+template <bool SMEM, bool COUNT>
+__global__ void __launch_bounds__(kPoolThreads, 1) traceKernelWP(const RenderParams p, const uint32_t sceneBytesAligned, const int traceLow)
 {
 	extern __shared__ __align__(128) float4 smemScene[];
 	__shared__ uint64_t mbar;
@@ -248,249 +258,313 @@ __global__ void __launch_bounds__(kThreads, 3) traceKernelV2(const RenderParams 
 		stageSceneToSmem(smemScene, p.scene.sceneBlob, (p.scene.nodeCount + p.scene.primCount) * 64u, &mbar);
 		sv.nodes = smemScene;
 		sv.prims = smemScene + size_t(p.scene.nodeCount) * 4;
+		sv.globalCount = p.scene.globalCount;
 	}
 	else
 	{
 		sv.nodes = p.scene.sceneBlob;
 		sv.prims = p.scene.sceneBlob + size_t(p.scene.nodeCount) * 4;
+		sv.globalCount = p.scene.globalCount;
 	}
+	constexpr uint32_t full = 0xffffffffu;
+	constexpr int K = kPoolSlots;
+	const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+	const uint32_t ltMask = (1u << lane) - 1u;
+	float *pool = reinterpret_cast<float *>(reinterpret_cast<char *>(smemScene) + sceneBytesAligned + size_t(warp) * kPoolBytesPerWarp);
+	uint32_t *poolU = reinterpret_cast<uint32_t *>(pool);
+	uint32_t *list = poolU + F_LIST * K;
+#define PF(field, slot) pool[(field) * K + (slot)]
+#define PU(field, slot) poolU[(field) * K + (slot)]
 
-	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t totalPixels = p.width * p.height;
 	const V3 camO = mk(p.cam.origin[0], p.cam.origin[1], p.cam.origin[2]);
 	constexpr float tMin = 0.001f;
 
-	// path state
-	uint32_t want = W_GEN;
-	bool hasPath = false, pendingMiss = false;
-	uint32_t pixel = kInvalid, sample = p.spp, sampleIdx = 0, bounce = 0, rz = 0, rw = 0;
-	V3 color = mk(0.0f, 0.0f, 0.0f);
-	V3 ro = camO, rd = mk(0.0f, 0.0f, 1.0f), thr = mk(1.0f, 1.0f, 1.0f), L = mk(0.0f, 0.0f, 0.0f);
-	// traversal state
+	// all slots start in `gen` without a pixel
+	PU(F_PIXEL, lane) = kInvalid; PU(F_PIXEL, lane + 32) = kInvalid;
+	PU(F_STATE, lane) = p.spp & kStateSampleMask; PU(F_STATE, lane + 32) = p.spp & kStateSampleMask;
+	PF(F_CX, lane) = 0.0f; PF(F_CY, lane) = 0.0f; PF(F_CZ, lane) = 0.0f;
+	PF(F_CX, lane + 32) = 0.0f; PF(F_CY, lane + 32) = 0.0f; PF(F_CZ, lane + 32) = 0.0f;
+	__syncwarp();
+	unsigned long long ready = 0ull, hit = 0ull, gen = ~0ull;
+
+	// the lane's in-flight traversal
+	int slot = -1;
+	V3 ro = camO, rd = mk(0.0f, 0.0f, 1.0f);
 	TravRay tr = makeTravRay(ro, rd);
+	int cur = kEmptyChild, parked = kEmptyChild, sp = 0, primBest = -1;
 	float tBest = FLT_MAX;
-	int primBest = -1, cur = 0, sp = 0;
-	uint32_t sceneBest = 0, leafPrim = 0, leafLeft = 0;
+	uint32_t sceneBest = 0;
 	int stack[kStackSize];
-	stack[0] = kSentinel;
 	uint32_t rays = 0, nodeVisits = 0, primTests = 0, shades = 0, misses = 0;
 
-	auto setCur = [&](int c)
+	auto buildList = [&](unsigned long long m) -> int
 	{
-		cur = c;
-		if (c == kSentinel)
-		{
-			pendingMiss = primBest < 0;
-			want = pendingMiss ? W_GEN : W_SHADE;
-		}
-		else if (c >= 0) want = W_NODE;
-		else
-		{
-			leafPrim = uint32_t(c) & kLeafStartMask;
-			leafLeft = (uint32_t(c) >> kLeafCountShift) & 15u;
-			want = classOfType((uint32_t(c) >> kLeafTypeShift) & 7u);
-			if (leafLeft == 0u) { cur = kSentinel; pendingMiss = primBest < 0; want = pendingMiss ? W_GEN : W_SHADE; } // empty leaf: never referenced by a hit box
-		}
+		const uint32_t lo = uint32_t(m), hi = uint32_t(m >> 32);
+		const uint32_t cl = __popc(lo);
+		if ((lo >> lane) & 1u) list[__popc(lo & ltMask)] = lane;
+		if ((hi >> lane) & 1u) list[cl + __popc(hi & ltMask)] = lane + 32u;
+		__syncwarp();
+		return int(cl + __popc(hi));
 	};
-	auto pop = [&]() -> int { return sp > 0 ? stack[--sp] : kSentinel; };
-	auto startRay = [&]()
+	auto slotMask = [&](bool pred, int s) -> unsigned long long
 	{
-		tr = makeTravRay(ro, rd);
-		sp = 0; tBest = FLT_MAX; primBest = -1; sceneBest = 0; cur = 0;
-		want = W_NODE;
-		++rays;
+		const uint32_t lo = (pred && s < 32) ? (1u << s) : 0u, hi = (pred && s >= 32) ? (1u << (s - 32)) : 0u;
+		return (unsigned long long)__reduce_or_sync(full, lo) | ((unsigned long long)__reduce_or_sync(full, hi) << 32);
 	};
-	auto primStep = [&](auto intersect)
+	auto testLeaf = [&](int leaf)
 	{
-		if (COUNT) ++primTests;
-		const float4 *pp = sv.prims + leafPrim * 4;
-		const float4 r0 = sv.ld(pp), r1 = sv.ld(pp + 1), r2 = sv.ld(pp + 2), meta = sv.ld(pp + 3);
-		V3 lo, ld;
-		toLocal(r0, r1, r2, ro, rd, lo, ld);
-		float t;
-		if (intersect(__float_as_uint(meta.x), lo, ld, tBest, t))
+		const uint32_t first = uint32_t(leaf) & kLeafStartMask;
+		const uint32_t count = (uint32_t(leaf) >> kLeafCountShift) & 15u;
+		for (uint32_t i = 0; i < count; ++i)
 		{
-			const uint32_t sceneIdx = __float_as_uint(meta.y);
-			if (!(t == tBest && primBest >= 0 && sceneIdx < sceneBest))
+			if (COUNT) ++primTests;
+			const float4 *pp = sv.prims + (first + i) * 4;
+			const float4 r0 = sv.ld(pp), r1 = sv.ld(pp + 1), r2 = sv.ld(pp + 2), meta = sv.ld(pp + 3);
+			V3 lo, ld;
+			toLocal(r0, r1, r2, ro, rd, lo, ld);
+			float t;
+			if (intersectLocal(__float_as_uint(meta.x), lo, ld, tMin, tBest, t))
 			{
-				tBest = t;
-				primBest = int(leafPrim);
-				sceneBest = sceneIdx;
+				const uint32_t sceneIdx = __float_as_uint(meta.y);
+				if (!(t == tBest && primBest >= 0 && sceneIdx < sceneBest))
+				{
+					tBest = t;
+					primBest = int(first + i);
+					sceneBest = sceneIdx;
+				}
 			}
 		}
-		--leafLeft;
-		++leafPrim;
-		if (leafLeft) want = classOfType(__float_as_uint(sv.ld(sv.prims + leafPrim * 4 + 3).x));
-		else setCur(pop());
 	};
 
 	while (true)
 	{
-		// ---- vote: how many lanes want each stage ----
-		const uint32_t bN = __ballot_sync(0xffffffffu, want == W_NODE);
-		const uint32_t bQ = __ballot_sync(0xffffffffu, want == W_PQ);
-		const uint32_t bF = __ballot_sync(0xffffffffu, want == W_PF);
-		const uint32_t bC = __ballot_sync(0xffffffffu, want == W_PC);
-		const uint32_t bS = __ballot_sync(0xffffffffu, want == W_SHADE);
-		const uint32_t bG = __ballot_sync(0xffffffffu, want == W_GEN);
-		if ((bN | bQ | bF | bC | bS | bG) == 0u) break;
-		uint32_t act = W_NODE;
-		int best = __popc(bN);
-		{ const int c = __popc(bQ); if (c > best) { best = c; act = W_PQ; } }
-		{ const int c = __popc(bF); if (c > best) { best = c; act = W_PF; } }
-		{ const int c = __popc(bC); if (c > best) { best = c; act = W_PC; } }
-		{ const int c = __popc(bS); if (c > best) { best = c; act = W_SHADE; } }
-		{ const int c = __popc(bG); if (c > best) { best = c; act = W_GEN; } }
+		const int nIn = __popc(__ballot_sync(full, slot >= 0));
+		const int nReady = __popcll(ready), nHit = __popcll(hit), nGen = __popcll(gen);
+		if (nIn + nReady + nHit + nGen == 0) break;
+		const int traceAvail = min(nIn + nReady, 32);
 
-		if (act == W_NODE)
+		if (nHit >= 32 || (traceAvail < traceLow && nHit > 0 && nHit >= nGen))
 		{
-			// ---- BVH-traverse stage: keep stepping while enough lanes are still walking interior nodes ----
-			do
-			{
-				if (want == W_NODE)
-				{
-					if (COUNT) ++nodeVisits;
-					const float4 *n = sv.nodes + cur * 4;
-					const float4 A = sv.ld(n), Bq = sv.ld(n + 1), C = sv.ld(n + 2);
-					const float4 Dq = sv.ld(n + 3);
-					bool hitA, hitB;
-					float nearA, nearB;
-					testNodeBoxes(A, Bq, C, tr, tMin, tBest, hitA, hitB, nearA, nearB);
-					const int cA = __float_as_int(Dq.x), cB = __float_as_int(Dq.y);
-					int next;
-					if (hitA && hitB)
-					{
-						const bool bFirst = nearB < nearA;
-						stack[sp++] = bFirst ? cA : cB;
-						next = bFirst ? cB : cA;
-					}
-					else if (hitA) next = cA;
-					else if (hitB) next = cB;
-					else next = pop();
-					setCur(next);
-				}
-			} while (__popc(__ballot_sync(0xffffffffu, want == W_NODE)) >= NODE_STICK);
-		}
-		else if (act == W_PQ)
-		{
-			// ---- intersect stage, quadric class ----
-			if (want == W_PQ) primStep([&](uint32_t type, V3 lo, V3 ld, float tMax, float &t) { return intersectQuadric(type, lo, ld, tMin, tMax, t); });
-		}
-		else if (act == W_PF)
-		{
-			if (want == W_PF) primStep([&](uint32_t type, V3 lo, V3 ld, float tMax, float &t) { return intersectFlat(type, lo, ld, tMin, tMax, t); });
-		}
-		else if (act == W_PC)
-		{
-			if (want == W_PC) primStep([&](uint32_t, V3 lo, V3 ld, float tMax, float &t) { return intersectCube(lo, ld, tMin, tMax, t); });
-		}
-		else if (act == W_SHADE)
-		{
-			// ---- shade / sample stage (trace.cu:136-151) ----
-			if (want == W_SHADE)
+			// ---------------- shade / sample stage (trace.cu:136-151) ----------------
+			const int n = min(buildList(hit), 32);
+			const bool mine = int(lane) < n;
+			const int s = mine ? int(list[lane]) : 0;
+			const unsigned long long taken = n == nHit ? hit : slotMask(mine, s);
+			hit &= ~taken;
+			bool cont = false;
+			if (mine)
 			{
 				if (COUNT) ++shades;
-				const Surface s = surfaceAt<SMEM>(sv, primBest, ro, rd, tBest);
-				const float4 *mp = reinterpret_cast<const float4 *>(p.scene.mats + primBest);
+				const V3 sro = mk(PF(F_OX, s), PF(F_OY, s), PF(F_OZ, s)), srd = mk(PF(F_DX, s), PF(F_DY, s), PF(F_DZ, s));
+				const int prim = int(PU(F_PRIM, s));
+				const Surface sf = surfaceAt<SMEM>(sv, prim, sro, srd, PF(F_T, s));
+				const float4 *mp = reinterpret_cast<const float4 *>(p.scene.mats + prim);
 				const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2);
-				L = L + thr * mk(m1.x, m1.y, m1.z);
+				V3 thr = mk(PF(F_TX, s), PF(F_TY, s), PF(F_TZ, s));
+				const V3 L = mk(PF(F_LX, s), PF(F_LY, s), PF(F_LZ, s)) + thr * mk(m1.x, m1.y, m1.z); // getEmitted, Material.inl:62-65
+				PF(F_LX, s) = L.x; PF(F_LY, s) = L.y; PF(F_LZ, s) = L.z;
 				V3 base = mk(m0.x, m0.y, m0.z);
 				const uint32_t tex = __float_as_uint(m2.x), mtype = __float_as_uint(m2.y);
 				if (tex != 0 && tex <= p.scene.texCount)
 				{
-					const V3 tap = texLookup(p.scene.textures, tex, s.u, s.v);
+					const V3 tap = texLookup(p.scene.textures, tex, sf.u, sf.v); // Material.inl:26-35
 					base = mk(fastPow(tap.x, 2.2f), fastPow(tap.y, 2.2f), fastPow(tap.z, 2.2f));
 				}
+				const uint32_t state = PU(F_STATE, s);
+				uint32_t bounce = (state >> kStateBounceShift) & 0x7fu;
 				float rnd0, rnd1;
-				if (bounce == 0) { rnd0 = uniform01(rz); rnd1 = uniform01(rw); }
-				else if (bounce & 1u)
+				if (bounce != 0u && (bounce & 1u))
 				{
-					const uint4 r = philox4x32_10(pixel, sampleIdx, (bounce + 1u) >> 1, 0u, p.seedLo, p.seedHi);
+					const uint4 r = philox4x32_10(PU(F_PIXEL, s), p.sampleOffset + (state & kStateSampleMask) * p.sampleStride, (bounce + 1u) >> 1, 0u, p.seedLo, p.seedHi);
 					rnd0 = uniform01(r.x); rnd1 = uniform01(r.y);
-					rz = r.z; rw = r.w;
+					PU(F_RZ, s) = r.z; PU(F_RW, s) = r.w;
 				}
-				else { rnd0 = uniform01(rz); rnd1 = uniform01(rw); }
+				else { rnd0 = uniform01(PU(F_RZ, s)); rnd1 = uniform01(PU(F_RW, s)); }
 				V3 wi, weight;
-				bool cont = sampleMaterial(mtype, base, m0.w, m1.w, s.n, rd, rnd0, rnd1, wi, weight);
+				cont = sampleMaterial(mtype, base, m0.w, m1.w, sf.n, srd, rnd0, rnd1, wi, weight);
 				if (cont)
 				{
-					thr = thr * weight;
-					ro = s.p;
-					rd = wi;
 					++bounce;
 					if (bounce >= p.maxBounces) cont = false;
 				}
-				if (cont) startRay();
-				else { want = W_GEN; pendingMiss = false; }
+				if (cont)
+				{
+					thr = thr * weight;
+					PF(F_TX, s) = thr.x; PF(F_TY, s) = thr.y; PF(F_TZ, s) = thr.z;
+					PF(F_OX, s) = sf.p.x; PF(F_OY, s) = sf.p.y; PF(F_OZ, s) = sf.p.z;
+					PF(F_DX, s) = wi.x; PF(F_DY, s) = wi.y; PF(F_DZ, s) = wi.z;
+					PU(F_STATE, s) = (state & ~(0x7fu << kStateBounceShift)) | (bounce << kStateBounceShift);
+				}
 			}
+			const unsigned long long contMask = slotMask(cont, s);
+			ready |= contMask;
+			gen |= taken & ~contMask; // F_PRIM stays >= 0: the generate stage will not look up the environment
+			__syncwarp();
+			continue;
 		}
-		else
+
+		if (nGen >= 32 || (traceAvail < traceLow && nGen > 0))
 		{
-			// ---- env-miss + accumulate + generate stage (trace.cu:115-134, :187-198) ----
-			const bool mine = want == W_GEN;
-			if (mine && hasPath)
+			// ---------------- env-miss + accumulate + generate stage (trace.cu:115-134, :187-198) ----------------
+			const int n = min(buildList(gen), 32);
+			const bool mine = int(lane) < n;
+			const int s = mine ? int(list[lane]) : 0;
+			const unsigned long long taken = n == nGen ? gen : slotMask(mine, s);
+			gen &= ~taken;
+			uint32_t pixel = kInvalid, sample = 0;
+			V3 color = mk(0.0f, 0.0f, 0.0f);
+			bool need = false;
+			if (mine)
 			{
-				if (pendingMiss)
+				const uint32_t state = PU(F_STATE, s);
+				pixel = PU(F_PIXEL, s);
+				sample = state & kStateSampleMask;
+				color = mk(PF(F_CX, s), PF(F_CY, s), PF(F_CZ, s));
+				if (state & kStateHasPath)
 				{
-					if (COUNT) ++misses;
-					if (p.scene.skybox != 0)
+					V3 L = mk(PF(F_LX, s), PF(F_LY, s), PF(F_LZ, s));
+					if (int(PU(F_PRIM, s)) < 0)
 					{
-						const float theta = acosf(rd.y), phi = atan2f(rd.z, rd.x);
-						const V3 sky = texLookup(p.scene.textures, p.scene.skybox, phi / (2.0f * PT_PI), theta / PT_PI);
-						L = L + thr * sky;
+						if (COUNT) ++misses;
+						if (p.scene.skybox != 0)
+						{
+							const V3 mrd = mk(PF(F_DX, s), PF(F_DY, s), PF(F_DZ, s)), thr = mk(PF(F_TX, s), PF(F_TY, s), PF(F_TZ, s));
+							const float theta = acosf(mrd.y), phi = atan2f(mrd.z, mrd.x);
+							const V3 sky = texLookup(p.scene.textures, p.scene.skybox, phi / (2.0f * PT_PI), theta / PT_PI);
+							L = L + thr * sky;
+						}
 					}
+					color = color + L;
+					++sample;
 				}
-				color = color + L;
-				++sample;
-				hasPath = false;
-			}
-			const bool need = mine && sample == p.spp;
-			if (need && pixel != kInvalid)
-			{
-				float4 out = make_float4(color.x, color.y, color.z, 1.0f);
-				if (!p.ignoreHistory)
+				need = sample >= p.spp;
+				if (need && pixel != kInvalid)
 				{
-					const float4 prev = p.accum[pixel];
-					out.x += prev.x; out.y += prev.y; out.z += prev.z;
+					float4 out = make_float4(color.x, color.y, color.z, 1.0f); // trace.cu:196-198
+					if (!p.ignoreHistory)
+					{
+						const float4 prev = p.accum[pixel];
+						out.x += prev.x; out.y += prev.y; out.z += prev.z;
+					}
+					p.accum[pixel] = out;
 				}
-				p.accum[pixel] = out;
 			}
-			const uint32_t needMask = __ballot_sync(0xffffffffu, need);
+			bool alive = mine;
+			const uint32_t needMask = __ballot_sync(full, need);
 			if (needMask)
 			{
 				const uint32_t leader = __ffs(needMask) - 1;
 				unsigned long long base = 0;
 				if (lane == leader) base = atomicAdd(&p.counters[kCtrWork], (unsigned long long)__popc(needMask));
-				base = __shfl_sync(0xffffffffu, base, leader);
+				base = __shfl_sync(full, base, leader);
 				if (need)
 				{
-					const unsigned long long m = base + __popc(needMask & ((1u << lane) - 1u));
-					if (m >= totalPixels) { want = W_DONE; pixel = kInvalid; }
+					const unsigned long long m = base + __popc(needMask & ltMask);
+					if (m >= totalPixels) alive = false; // slot retires: in no mask from now on
 					else { pixel = uint32_t(m); sample = 0; color = mk(0.0f, 0.0f, 0.0f); }
 				}
 			}
-			if (mine && want == W_GEN)
+			if (alive)
 			{
-				sampleIdx = p.sampleOffset + sample * p.sampleStride;
+				const uint32_t sampleIdx = p.sampleOffset + sample * p.sampleStride;
 				const uint4 r = philox4x32_10(pixel, sampleIdx, 0u, 0u, p.seedLo, p.seedHi);
 				const uint32_t px = pixel % p.width, py = pixel / p.width;
-				const float u = divExact(float(px) + uniform01(r.x), float(p.width));
+				const float u = divExact(float(px) + uniform01(r.x), float(p.width)); // trace.cu:190
 				const float v = divExact(float(py) + uniform01(r.y), float(p.height));
-				rz = r.z; rw = r.w;
-				ro = camO;
-				rd = cameraDir(p.cam, u, v);
-				thr = mk(1.0f, 1.0f, 1.0f);
-				L = mk(0.0f, 0.0f, 0.0f);
-				bounce = 0;
-				hasPath = true;
-				startRay();
+				const V3 d = cameraDir(p.cam, u, v);
+				PF(F_OX, s) = camO.x; PF(F_OY, s) = camO.y; PF(F_OZ, s) = camO.z;
+				PF(F_DX, s) = d.x; PF(F_DY, s) = d.y; PF(F_DZ, s) = d.z;
+				PF(F_TX, s) = 1.0f; PF(F_TY, s) = 1.0f; PF(F_TZ, s) = 1.0f;
+				PF(F_LX, s) = 0.0f; PF(F_LY, s) = 0.0f; PF(F_LZ, s) = 0.0f;
+				PF(F_CX, s) = color.x; PF(F_CY, s) = color.y; PF(F_CZ, s) = color.z;
+				PU(F_RZ, s) = r.z; PU(F_RW, s) = r.w;
+				PU(F_PIXEL, s) = pixel;
+				PU(F_STATE, s) = kStateHasPath | sample;
+			}
+			ready |= slotMask(alive, s);
+			__syncwarp();
+			continue;
+		}
+
+		// ---------------- BVH-traverse + intersect stage (trace.cu:112, hitBVH :28-98) ----------------
+		{
+			const uint32_t needRay = __ballot_sync(full, slot < 0);
+			if (needRay != 0u && ready != 0ull)
+			{
+				const int nList = buildList(ready);
+				const int r = __popc(needRay & ltMask);
+				const bool take = slot < 0 && r < nList;
+				if (take)
+				{
+					slot = int(list[r]);
+					ro = mk(PF(F_OX, slot), PF(F_OY, slot), PF(F_OZ, slot));
+					rd = mk(PF(F_DX, slot), PF(F_DY, slot), PF(F_DZ, slot));
+					tr = makeTravRay(ro, rd);
+					stack[0] = kEmptyChild; // sentinel: a leaf reference with zero primitives
+					sp = 1; cur = 0; parked = kEmptyChild;
+					tBest = FLT_MAX; primBest = -1; sceneBest = 0;
+					++rays;
+					for (uint32_t g = 0; g < sv.globalCount; ++g)
+					{
+						if (COUNT) ++primTests;
+						testPrim<SMEM>(sv, g, ro, rd, tMin, tBest, primBest, sceneBest);
+					}
+				}
+				ready &= ~slotMask(take, slot);
+				__syncwarp();
 			}
 		}
+		bool done;
+		do
+		{
+			while (cur >= 0)
+			{
+				if (COUNT) ++nodeVisits;
+				const float4 *n = sv.nodes + cur * 4;
+				const float4 A = sv.ld(n), Bq = sv.ld(n + 1), C = sv.ld(n + 2);
+				const float4 Dq = sv.ld(n + 3);
+				bool hitA, hitB;
+				float nearA, nearB;
+				testNodeBoxes(A, Bq, C, tr, tMin, tBest, hitA, hitB, nearA, nearB);
+				const int cA = __float_as_int(Dq.x), cB = __float_as_int(Dq.y);
+				if (hitA && hitB)
+				{
+					const bool bFirst = nearB < nearA;
+					stack[sp++] = bFirst ? cA : cB;
+					cur = bFirst ? cB : cA;
+				}
+				else if (hitA) cur = cA;
+				else if (hitB) cur = cB;
+				else cur = stack[--sp];
+				// park the first leaf found and keep walking (the sentinel is never parked: it ends the walk)
+				if (cur < 0 && cur != kEmptyChild && parked == kEmptyChild)
+				{
+					parked = cur;
+					cur = stack[--sp];
+				}
+			}
+			if (parked != kEmptyChild) { testLeaf(parked); parked = kEmptyChild; }
+			if (cur != kEmptyChild) { testLeaf(cur); cur = stack[--sp]; }
+			done = slot >= 0 && cur == kEmptyChild;
+		} while (!__any_sync(full, done) && __any_sync(full, slot >= 0));
+
+		if (__any_sync(full, done))
+		{
+			if (done) { PF(F_T, slot) = tBest; PU(F_PRIM, slot) = uint32_t(primBest); }
+			const unsigned long long fin = slotMask(done, slot), finHit = slotMask(done && primBest >= 0, slot);
+			hit |= finHit;
+			gen |= fin & ~finHit;
+			if (done) slot = -1;
+			__syncwarp();
+		}
 	}
+#undef PF
+#undef PU
 
 	unsigned long long r64 = rays;
 #pragma unroll
-	for (int o = 16; o > 0; o >>= 1) r64 += __shfl_xor_sync(0xffffffffu, r64, o);
+	for (int o = 16; o > 0; o >>= 1) r64 += __shfl_xor_sync(full, r64, o);
 	if (lane == 0) atomicAdd(&p.counters[kCtrRays], r64);
 	if (COUNT)
 	{
@@ -499,7 +573,7 @@ __global__ void __launch_bounds__(kThreads, 3) traceKernelV2(const RenderParams 
 		for (int k = 0; k < 4; ++k)
 		{
 #pragma unroll
-			for (int o = 16; o > 0; o >>= 1) c[k] += __shfl_xor_sync(0xffffffffu, c[k], o);
+			for (int o = 16; o > 0; o >>= 1) c[k] += __shfl_xor_sync(full, c[k], o);
 			if (lane == 0) atomicAdd(&p.counters[kCtrNodes + k], c[k]);
 		}
 	}
@@ -513,6 +587,7 @@ __global__ void __launch_bounds__(kThreads) primaryKernel(SceneDev scene, Camera
 	SceneView<false> sv;
 	sv.nodes = scene.sceneBlob;
 	sv.prims = scene.sceneBlob + size_t(scene.nodeCount) * 4;
+	sv.globalCount = scene.globalCount;
 	const uint32_t total = width * height;
 	uint32_t nv = 0, pt = 0;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
@@ -533,6 +608,7 @@ __global__ void __launch_bounds__(kThreads) traceRaysKernel(SceneDev scene, uint
 	SceneView<false> sv;
 	sv.nodes = scene.sceneBlob;
 	sv.prims = scene.sceneBlob + size_t(scene.nodeCount) * 4;
+	sv.globalCount = scene.globalCount;
 	uint32_t nv = 0, pt = 0;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
 	{
@@ -588,8 +664,31 @@ static int launchKernel(K kern, const RenderParams &p, const LaunchConfig &cfg, 
 	return 1;
 }
 
+template <typename K>
+static int launchPool(K kern, const RenderParams &p, const LaunchConfig &cfg, size_t sceneBytesAligned, int warps, cudaStream_t stream)
+{
+	const size_t smemBytes = sceneBytesAligned + size_t(warps) * kPoolBytesPerWarp;
+	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemBytes));
+	const int traceLow = cfg.traceLow > 0 ? cfg.traceLow : 24;
+	kern<<<cfg.smCount, warps * 32, smemBytes, stream>>>(p, uint32_t(sceneBytesAligned), traceLow);
+	return 1;
+}
+
 int launchTrace(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t stream, int *usedSmem)
 {
+	if ((cfg.variant == 0 || cfg.variant == 6) && p.spp <= kStateSampleMask && p.maxBounces <= 0x7fu)
+	{
+		// warp-pool wavefront: one CTA per SM, as many warps as the pools (and the scene copy) leave room for
+		const size_t sceneBytes = (size_t(p.scene.nodeCount) + p.scene.primCount) * 64;
+		const size_t aligned = (sceneBytes + 127) & ~size_t(127);
+		const size_t avail = cfg.maxSmemOptin > 2048 ? cfg.maxSmemOptin - 2048 : 0;
+		const int maxWarps = cfg.poolWarps > 0 ? std::min(cfg.poolWarps, kPoolThreads / 32) : kPoolThreads / 32;
+		const bool smem = cfg.smemScene && aligned + size_t(16) * kPoolBytesPerWarp <= avail;
+		const int warps = int(std::min<size_t>(size_t(maxWarps), (avail - (smem ? aligned : 0)) / kPoolBytesPerWarp));
+		if (usedSmem) *usedSmem = smem ? 1 : 0;
+		if (smem) return cfg.countWork ? launchPool(traceKernelWP<true, true>, p, cfg, aligned, warps, stream) : launchPool(traceKernelWP<true, false>, p, cfg, aligned, warps, stream);
+		return cfg.countWork ? launchPool(traceKernelWP<false, true>, p, cfg, 0, warps, stream) : launchPool(traceKernelWP<false, false>, p, cfg, 0, warps, stream);
+	}
 	const size_t sceneBytes = (size_t(p.scene.nodeCount) + p.scene.primCount) * 64;
 	// leave room for 2+ CTAs per SM when the scene is small; a scene larger than the opt-in limit stays in L2/HBM
 	const bool smem = cfg.smemScene && sceneBytes + 1024 <= cfg.maxSmemOptin;
@@ -602,9 +701,7 @@ int launchTrace(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t str
 	{
 	case 1: return PT_PICK(traceKernel, , 0);      // per-lane if/else traversal
 	case 4: return PT_PICK(traceKernel, , 1);      // while-while traversal
-	case 2: return PT_PICK(traceKernelV2, , 8);    // stage-voting warp scheduler
-	case 3: return PT_PICK(traceKernelV2, , 16);
-	default: return PT_PICK(traceKernel, , 2);     // while-while + speculative leaf parking (fastest measured)
+	default: return PT_PICK(traceKernel, , 2);     // 5: while-while + speculative leaf parking
 	}
 #undef PT_PICK
 }

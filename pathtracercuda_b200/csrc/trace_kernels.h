@@ -15,6 +15,7 @@ struct SceneDev
 	const Mat *mats = nullptr;
 	const TexDesc *textures = nullptr;
 	uint32_t nodeCount = 0, primCount = 0, texCount = 0, skybox = 0;
+	uint32_t globalCount = 0; // prims[0..globalCount): tested by every ray before the traversal (pt_types.h)
 };
 
 struct RenderParams
@@ -34,7 +35,9 @@ struct LaunchConfig
 	int smCount = 148;
 	int smemScene = 1;   // stage the scene in shared memory when it fits
 	int countWork = 0;   // node/prim/shade/miss counters
-	int variant = 0;     // kernel variant (0 = default)
+	int variant = 0;     // kernel variant (0 = default = 6: warp-pool wavefront; 1/4/5: per-lane megakernel)
+	int traceLow = 0;    // warp-pool: run shade/generate early when fewer than this many lanes could traverse (0 = 24)
+	int poolWarps = 0;   // warp-pool: warps per CTA (0 = as many as fit, <= 24)
 	size_t maxSmemOptin = 0;
 };
 

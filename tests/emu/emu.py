@@ -60,6 +60,11 @@ class Emu:
         self.L.emu_scene_arrays(self.s, _p(nd), _p(pr))
         return nd, pr
 
+    def global_count(self):
+        self.L.emu_global_count.restype = C.c_uint32
+        self.L.emu_global_count.argtypes = [C.c_void_p]
+        return int(self.L.emu_global_count(self.s))
+
     def add_texture(self, img):
         img = np.ascontiguousarray(img)
         is_hdr = img.dtype == np.float32

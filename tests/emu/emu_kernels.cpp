@@ -53,10 +53,13 @@ struct EmuScene
 		SceneView<false> sv;
 		sv.nodes = blob.data();
 		sv.prims = blob.data() + cs.nodes.size() * 4;
+		sv.globalCount = cs.globalCount;
 		return sv;
 	}
 };
 } // namespace
+
+static uint64_t g_lastWork[2] = { 0, 0 };
 
 extern "C"
 {
@@ -84,6 +87,7 @@ uint32_t emu_add_texture(void *p, uint32_t w, uint32_t h, int isHdr, const void 
 	return ++s->texCount;
 }
 void emu_set_skybox(void *p, uint32_t h) { ((EmuScene *)p)->skybox = h; }
+uint32_t emu_global_count(void *p) { return ((EmuScene *)p)->cs.globalCount; }
 void emu_scene_info(void *p, uint32_t *nodes, uint32_t *depth, uint32_t *leaves)
 {
 	EmuScene *s = (EmuScene *)p;
@@ -156,8 +160,8 @@ uint64_t emu_render(void *p, const pt_camera_desc *cd, uint32_t width, uint32_t 
 	const uint32_t seedLo = (uint32_t)seed, seedHi = (uint32_t)(seed >> 32);
 	const float invW = 1.0f / float(width), invH = 1.0f / float(height);
 	const V3 camO = mk(cam.origin[0], cam.origin[1], cam.origin[2]);
-	uint64_t raysTot = 0;
-#pragma omp parallel for schedule(dynamic, 1) reduction(+ : raysTot)
+	uint64_t raysTot = 0, nvTot = 0, ptTot = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : raysTot, nvTot, ptTot)
 	for (int y = 0; y < (int)height; ++y)
 		for (uint32_t x = 0; x < width; ++x)
 		{
@@ -175,7 +179,8 @@ uint64_t emu_render(void *p, const pt_camera_desc *cd, uint32_t width, uint32_t 
 				{
 					++raysTot;
 					uint32_t nv = 0, pt = 0;
-					const Hit h = closestHit<false, false>(sv, ro, rd, 0.001f, nv, pt);
+					const Hit h = closestHit<false, true>(sv, ro, rd, 0.001f, nv, pt);
+					nvTot += nv; ptTot += pt;
 					if (h.prim < 0)
 					{
 						if (s->skybox != 0)
@@ -215,6 +220,9 @@ uint64_t emu_render(void *p, const pt_camera_desc *cd, uint32_t width, uint32_t 
 			if (add) { color.x += a[0]; color.y += a[1]; color.z += a[2]; }
 			a[0] = color.x; a[1] = color.y; a[2] = color.z; a[3] = 1.0f;
 		}
+	g_lastWork[0] = nvTot; g_lastWork[1] = ptTot;
 	return raysTot;
 }
+// node visits / primitive tests of the last emu_render (BVH quality experiments)
+void emu_last_work(uint64_t *out) { out[0] = g_lastWork[0]; out[1] = g_lastWork[1]; }
 }

@@ -117,6 +117,11 @@ def test_image_codecs(tmp_path):
         assert open(f, "rb").read().startswith(b"#?RADIANCE\n# Written by stb_image_write.h\nFORMAT=32-bit_rle_rgbe\nEXPOSURE=          1.0000000000000\n\n-Y 6 +X ")
 
 
+def _area(b):
+    e = np.maximum(b[1] - b[0], 0)
+    return 2 * (e[0] * e[1] + e[0] * e[2] + e[1] * e[2])
+
+
 def _validate_bvh(objs, max_leaf=4):
     E = Emu(objs, max_leaf)
     nodes, prims = E.arrays()
@@ -157,7 +162,18 @@ def _validate_bvh(objs, max_leaf=4):
         return out, dmax
 
     _, depth = walk(0, 0)
-    assert (seen == 1).all(), "every primitive in exactly one leaf (reference BVH::validate)"
+    # primitives that span the scene are hoisted out of the tree and tested by every ray first: the first G records
+    G = E.global_count()
+    assert G <= 8 and G < len(objs)
+    scene_area = _area(np.array([boxes[:, :3].min(0), boxes[:, 3:].max(0)]))
+    for k in range(len(objs)):
+        a = _area(np.array([boxes[prims[k, 13]][:3], boxes[prims[k, 13]][3:]]))
+        if k < G:
+            seen[prims[k, 13]] += 1
+            assert a >= 0.25 * scene_area * (1 - 1e-5)
+        elif G < 8 and G < len(objs) - 1:
+            assert a < 0.25 * scene_area * (1 + 1e-5), "a scene-spanning primitive was left in the tree"
+    assert (seen == 1).all(), "every primitive in exactly one leaf or hoisted (reference BVH::validate)"
     info = E.info()
     assert info[0] == len(nodes) and depth <= info[1] + 1
     return info

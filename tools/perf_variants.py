@@ -32,4 +32,4 @@ for scene in scenes:
                 ref_img[scene] = img
             same = bool(np.array_equal(ref_img[scene].view(np.uint32), img.view(np.uint32)))
             print(json.dumps({"scene": scene, "variant": v, "ms": round(best, 3), "Mrays_s": round(st.rays / best / 1e3, 1), "Msamples_s": round(st.samples / best / 1e3, 1),
-                              "extra": extra, "bit_identical_to_first": same, "maxdiff": float(np.abs(ref_img[scene] - img).max())}), flush=True)
+                              "extra": extra, "bvh_nodes": st.bvh_nodes, "nodes_per_ray": round(st.node_visits / max(st.rays, 1), 2), "prims_per_ray": round(st.prim_tests / max(st.rays, 1), 2), "bit_identical_to_first": same, "maxdiff": float(np.abs(ref_img[scene] - img).max())}), flush=True)
