@@ -57,6 +57,7 @@ struct pt_context
 	uint32_t framesPerSpp = 0, maxBounces = 5, maxLeaf = 4;
 	LaunchConfig launch;
 	pt_stats stats;
+	unsigned long long rawCounters[ptb::kCtrCount] = {};
 };
 
 #define CK(expr)                                                                                                      \
@@ -276,6 +277,8 @@ int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ign
 		unsigned long long h[kCtrCount];
 		CK(cudaMemcpy(h, c->counters, sizeof h, cudaMemcpyDeviceToHost));
 		c->stats.samples = (unsigned long long)c->width * c->height * spp;
+		memcpy(c->rawCounters, h, sizeof h);
+		if (h[kCtrError] != 0) return setError(PT_E_CUDA, "pt_render: wavefront scheduler watchdog fired (code " + std::to_string(h[kCtrError]) + ")");
 		c->stats.rays = h[kCtrRays];
 		c->stats.node_visits = h[kCtrNodes];
 		c->stats.prim_tests = h[kCtrPrims];
@@ -354,8 +357,18 @@ int pt_set_option(pt_context *c, const char *key, double value)
 	else if (k == "max_global") c->maxGlobal = uint32_t(value < 0 ? 0 : value);
 	else if (k == "trace_low") c->launch.traceLow = int(value);
 	else if (k == "pool_warps") c->launch.poolWarps = int(value);
+	else if (k == "pool_slots") c->launch.poolSlots = int(value);
 	else return setError(PT_E_INVALID, "pt_set_option: unknown option " + k);
 	return PT_OK;
+}
+
+/* debugging aid (not in the header): raw device counters of the last pt_render, see trace_kernels.h kCtr* */
+extern "C" int pt_debug_counters(const pt_context *c, unsigned long long *out, int n)
+{
+	if (!c || !out) return 0;
+	const int m = n < int(kCtrCount) ? n : int(kCtrCount);
+	for (int i = 0; i < m; ++i) out[i] = c->rawCounters[i];
+	return m;
 }
 
 int pt_get_stats(const pt_context *c, pt_stats *out)

@@ -1,0 +1,46 @@
+// trace_common.cuh — pieces shared by the trace kernels (trace_kernels.cu, trace_wavefront.cu).
+#pragma once
+#include "trace_device.cuh"
+
+namespace ptb
+{
+
+constexpr int kThreads = 256;
+constexpr uint32_t kInvalid = 0xffffffffu;
+
+// ---------------------------------------------------------------------------------------------------------------
+// TMA bulk copy of the scene blob into shared memory (cp.async.bulk + mbarrier), one elected thread per CTA
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void stageSceneToSmem(void *smemDst, const void *gsrc, uint32_t bytes, uint64_t *mbar)
+{
+	const uint32_t mbarAddr = uint32_t(__cvta_generic_to_shared(mbar));
+	if (threadIdx.x == 0)
+	{
+		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbarAddr));
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbarAddr), "r"(bytes) : "memory");
+		uint32_t done = 0;
+		const uint32_t dst = uint32_t(__cvta_generic_to_shared(smemDst));
+		while (done < bytes)
+		{
+			const uint32_t chunk = min(bytes - done, 32768u);
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + done),
+			             "l"(reinterpret_cast<const char *>(gsrc) + done), "r"(chunk), "r"(mbarAddr)
+			             : "memory");
+			done += chunk;
+		}
+	}
+	// everyone waits for phase 0 of the barrier to complete (all bytes landed)
+	uint32_t ready = 0;
+	while (!ready)
+	{
+		asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ready) : "r"(mbarAddr), "r"(0u) : "memory");
+	}
+}
+
+
+} // namespace ptb

@@ -16,48 +16,11 @@
 //     two flat shapes share another: 3 divergent classes instead of 7;
 //   * normals, UVs, the tangent frame and the material fetch happen once per path segment at the closest hit, not once
 //     per accepted candidate (Hittable.inl:129-142).
-#include "trace_device.cuh"
+#include "trace_common.cuh"
 #include <algorithm>
 
 namespace ptb
 {
-
-constexpr int kThreads = 256;
-constexpr uint32_t kInvalid = 0xffffffffu;
-
-// ---------------------------------------------------------------------------------------------------------------
-// TMA bulk copy of the scene blob into shared memory (cp.async.bulk + mbarrier), one elected thread per CTA
-// ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void stageSceneToSmem(void *smemDst, const void *gsrc, uint32_t bytes, uint64_t *mbar)
-{
-	const uint32_t mbarAddr = uint32_t(__cvta_generic_to_shared(mbar));
-	if (threadIdx.x == 0)
-	{
-		asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbarAddr));
-		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-	}
-	__syncthreads();
-	if (threadIdx.x == 0)
-	{
-		asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbarAddr), "r"(bytes) : "memory");
-		uint32_t done = 0;
-		const uint32_t dst = uint32_t(__cvta_generic_to_shared(smemDst));
-		while (done < bytes)
-		{
-			const uint32_t chunk = min(bytes - done, 32768u);
-			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + done),
-			             "l"(reinterpret_cast<const char *>(gsrc) + done), "r"(chunk), "r"(mbarAddr)
-			             : "memory");
-			done += chunk;
-		}
-	}
-	// everyone waits for phase 0 of the barrier to complete (all bytes landed)
-	uint32_t ready = 0;
-	while (!ready)
-	{
-		asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(ready) : "r"(mbarAddr), "r"(0u) : "memory");
-	}
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // the trace kernel
@@ -676,7 +639,12 @@ static int launchPool(K kern, const RenderParams &p, const LaunchConfig &cfg, si
 
 int launchTrace(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t stream, int *usedSmem)
 {
-	if ((cfg.variant == 0 || cfg.variant == 6) && p.spp <= kStateSampleMask && p.maxBounces <= 0x7fu)
+	if (cfg.variant == 0 || cfg.variant == 7)
+	{
+		const int n = launchTraceWavefront(p, cfg, stream, usedSmem);
+		if (n > 0) return n;
+	}
+	if ((cfg.variant == 0 || cfg.variant == 6 || cfg.variant == 7) && p.spp <= kStateSampleMask && p.maxBounces <= 0x7fu)
 	{
 		// warp-pool wavefront: one CTA per SM, as many warps as the pools (and the scene copy) leave room for
 		const size_t sceneBytes = (size_t(p.scene.nodeCount) + p.scene.primCount) * 64;

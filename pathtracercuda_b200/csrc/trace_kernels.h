@@ -7,7 +7,10 @@ namespace ptb
 {
 
 // counters[] layout (device, unsigned long long)
-enum { kCtrWork = 0, kCtrRays = 1, kCtrNodes = 2, kCtrPrims = 3, kCtrShades = 4, kCtrMisses = 5, kCtrCount = 8 };
+enum { kCtrWork = 0, kCtrRays = 1, kCtrNodes = 2, kCtrPrims = 3, kCtrShades = 4, kCtrMisses = 5, kCtrError = 7,
+       // scheduler statistics of the wavefront kernel (count_work = 1): stage executions and the slots they served
+       kCtrTraceRounds = 8, kCtrTraceWalkers = 9, kCtrNodeIters = 10, kCtrShadeExec = 11, kCtrShadeSlots = 12, kCtrGenExec = 13, kCtrGenSlots = 14,
+       kCtrLeafExec = 15, kCtrLeafSlots = 16, kCtrIdle = 17, kCtrBlocked = 18, kCtrRefills = 19, kCtrRefillSlots = 20, kCtrCount = 24 };
 
 struct SceneDev
 {
@@ -35,14 +38,16 @@ struct LaunchConfig
 	int smCount = 148;
 	int smemScene = 1;   // stage the scene in shared memory when it fits
 	int countWork = 0;   // node/prim/shade/miss counters
-	int variant = 0;     // kernel variant (0 = default = 6: warp-pool wavefront; 1/4/5: per-lane megakernel)
+	int variant = 0;     // kernel variant (0 = default = 7: CTA-pool wavefront; 6: warp-pool wavefront; 1/4/5: per-lane megakernel)
 	int traceLow = 0;    // warp-pool: run shade/generate early when fewer than this many lanes could traverse (0 = 24)
 	int poolWarps = 0;   // warp-pool: warps per CTA (0 = as many as fit, <= 24)
+	int poolSlots = 0;   // CTA-pool wavefront: path slots per CTA (0 = 1280 with the scene in shared memory, 1536 without)
 	size_t maxSmemOptin = 0;
 };
 
 // Returns the number of kernels launched; *usedSmem = 1 when the scene was staged in shared memory.
 int launchTrace(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t stream, int *usedSmem);
+int launchTraceWavefront(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t stream, int *usedSmem); // trace_wavefront.cu; 0 = not applicable
 int launchPrimary(const SceneDev &scene, const CameraDev &cam, uint32_t width, uint32_t height, int32_t *hitIndex, float *hitT, cudaStream_t stream);
 int launchTraceRays(const SceneDev &scene, size_t n, const float *origins, const float *directions, float tMin, int32_t *hitIndex, float *hitT,
                     float *hitNormal, cudaStream_t stream);

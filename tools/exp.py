@@ -1,0 +1,38 @@
+#!/usr/bin/env python3
+"""Timing experiments: tools/exp.py scene variant spp [key=value ...]  (keys: any pt_set_option key, plus nosky=1, w=, h=)"""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import pathtracercuda_b200 as pt
+scene, variant, spp = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+kv = dict(a.split("=") for a in sys.argv[4:])
+W, H = int(kv.pop("w", 1920)), int(kv.pop("h", 1080))
+nosky = int(kv.pop("nosky", 0))
+with pt.Pathtracer(W, H) as P:
+    for k in ("max_global", "max_leaf"):
+        if k in kv:
+            P.setOption(k, float(kv.pop(k)))
+    cam = P.loadSceneFile(f"{pt.ASSETS}/scenes/{scene}.json", cwd=pt.ASSETS)
+    P.setOption("variant", variant)
+    for k, v in kv.items():
+        P.setOption(k, float(v))
+    if nosky:
+        P.setSkyboxTextureHandle(0)
+    P.render(cam, 8, True)
+    best = min((P.render(cam, spp, True), P.getTiming())[1] for _ in range(3))
+    st = P.stats()
+    print(json.dumps({"scene": scene, "variant": variant, "spp": spp, "opts": sys.argv[4:], "ms": round(best, 3), "Mrays_s": round(st.rays / best / 1e3, 1),
+                      "rays_per_sample": round(st.rays / st.samples, 3), "nodes_per_ray": round(st.node_visits / st.rays, 2), "prims_per_ray": round(st.prim_tests / st.rays, 2),
+                      "bvh_nodes": st.bvh_nodes, "smem": st.scene_in_smem}), flush=True)
+    import ctypes as C
+    raw = (C.c_ulonglong * 24)()
+    if hasattr(P.L, "pt_debug_counters") and P.L.pt_debug_counters(P.h, raw, 24) == 24 and raw[8]:
+        r = list(raw)
+        names = ["traceRounds", "traceWalkers", "nodeIters", "shadeExec", "shadeSlots", "genExec", "genSlots", "leafExec", "leafSlots", "idle", "blocked", "refills", "refillSlots"]
+        d = dict(zip(names, r[8:21]))
+        rays = st.rays
+        print(json.dumps({"rays_per_traceRound": round(rays / max(d["traceRounds"], 1), 2), "walkers_at_round_start": round(d["traceWalkers"] / max(d["traceRounds"], 1), 2),
+                          "nodeIters_per_round": round(d["nodeIters"] / max(d["traceRounds"], 1), 2), "walkers_per_nodeIter": round(st.node_visits / max(d["nodeIters"], 1), 2),
+                          "shade_slots_per_exec": round(d["shadeSlots"] / max(d["shadeExec"], 1), 2), "gen_slots_per_exec": round(d["genSlots"] / max(d["genExec"], 1), 2),
+                          "leaf_slots_per_exec": round(d["leafSlots"] / max(d["leafExec"], 1), 2), "leaf_slots_per_ray": round(d["leafSlots"] / rays, 3),
+                          "idle_per_kray": round(1e3 * d["idle"] / rays, 3), "blocked_rounds_frac": round(d["blocked"] / max(d["traceRounds"], 1), 4),
+                          "refill_slots_per_refill": round(d["refillSlots"] / max(d["refills"], 1), 2), "raw": d}))
