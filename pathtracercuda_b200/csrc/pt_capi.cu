@@ -357,6 +357,8 @@ int pt_set_option(pt_context *c, const char *key, double value)
 	else if (k == "max_global") c->maxGlobal = uint32_t(value < 0 ? 0 : value);
 	else if (k == "trace_low") c->launch.traceLow = int(value);
 	else if (k == "pool_warps") c->launch.poolWarps = int(value);
+	else if (k == "trace_warps") c->launch.traceWarps = int(value);
+	else if (k == "ready_low") c->launch.readyLow = int(value);
 	else if (k == "pool_slots") c->launch.poolSlots = int(value);
 	else return setError(PT_E_INVALID, "pt_set_option: unknown option " + k);
 	return PT_OK;

@@ -41,6 +41,8 @@ struct LaunchConfig
 	int variant = 0;     // kernel variant (0 = default = 7: CTA-pool wavefront; 6: warp-pool wavefront; 1/4/5: per-lane megakernel)
 	int traceLow = 0;    // warp-pool: run shade/generate early when fewer than this many lanes could traverse (0 = 24)
 	int poolWarps = 0;   // warp-pool: warps per CTA (0 = as many as fit, <= 24)
+	int traceWarps = 0;  // wavefront: warps per CTA that only traverse (0 = half of them); the others run the other stages
+	int readyLow = -1;   // wavefront: stage warps run partial batches while the READY queue holds fewer rays than this (-1 = 128)
 	int poolSlots = 0;   // CTA-pool wavefront: path slots per CTA (0 = 1280 with the scene in shared memory, 1536 without)
 	size_t maxSmemOptin = 0;
 };
