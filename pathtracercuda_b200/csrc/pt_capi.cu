@@ -356,6 +356,7 @@ int pt_set_option(pt_context *c, const char *key, double value)
 	else if (k == "variant") c->launch.variant = int(value);
 	else if (k == "max_global") c->maxGlobal = uint32_t(value < 0 ? 0 : value);
 	else if (k == "trace_low") c->launch.traceLow = int(value);
+	else if (k == "node_low") c->launch.nodeLow = int(value);
 	else if (k == "pool_warps") c->launch.poolWarps = int(value);
 	else if (k == "trace_warps") c->launch.traceWarps = int(value);
 	else if (k == "ready_low") c->launch.readyLow = int(value);

@@ -38,8 +38,10 @@ struct LaunchConfig
 	int smCount = 148;
 	int smemScene = 1;   // stage the scene in shared memory when it fits
 	int countWork = 0;   // node/prim/shade/miss counters
-	int variant = 0;     // kernel variant (0 = default = 7: CTA-pool wavefront; 6: warp-pool wavefront; 1/4/5: per-lane megakernel)
+	int variant = 0;     // kernel variant (0 = default = 5: persistent per-lane kernel, while-while + leaf parking; 1/4: its simpler traversals;
+	                     //  6: warp-pool wavefront, 7: CTA-pool warp-specialised wavefront - both measured slower)
 	int traceLow = 0;    // warp-pool: run shade/generate early when fewer than this many lanes could traverse (0 = 24)
+	int nodeLow = 0;     // warp-pool: the node loop leaves when fewer than this many lanes are still walking (0 = 24)
 	int poolWarps = 0;   // warp-pool: warps per CTA (0 = as many as fit, <= 24)
 	int traceWarps = 0;  // wavefront: warps per CTA that only traverse (0 = half of them); the others run the other stages
 	int readyLow = -1;   // wavefront: stage warps run partial batches while the READY queue holds fewer rays than this (-1 = 128)
@@ -49,6 +51,7 @@ struct LaunchConfig
 
 // Returns the number of kernels launched; *usedSmem = 1 when the scene was staged in shared memory.
 int launchTrace(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t stream, int *usedSmem);
+int launchTraceWarpPool(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t stream, int *usedSmem);   // trace_warppool.cu; 0 = not applicable
 int launchTraceWavefront(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t stream, int *usedSmem); // trace_wavefront.cu; 0 = not applicable
 int launchPrimary(const SceneDev &scene, const CameraDev &cam, uint32_t width, uint32_t height, int32_t *hitIndex, float *hitT, cudaStream_t stream);
 int launchTraceRays(const SceneDev &scene, size_t n, const float *origins, const float *directions, float tMin, int32_t *hitIndex, float *hitT,

@@ -630,7 +630,7 @@ template <typename K>
 static int launchWf(K kern, const RenderParams &p, const LaunchConfig &cfg, const WfLayout &lay, cudaStream_t stream)
 {
 	cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(lay.total()));
-	const int nodeLow = cfg.traceLow > 0 ? cfg.traceLow : 24;
+	const int nodeLow = cfg.nodeLow > 0 ? cfg.nodeLow : 24;
 	kern<<<cfg.smCount, lay.warps * 32, lay.total(), stream>>>(p, lay, nodeLow, cfg.readyLow >= 0 ? cfg.readyLow : 128);
 	return 1;
 }

@@ -155,7 +155,7 @@ def test_kernel_variants_bit_identical():
     """every scheduling variant of the trace kernel computes the same image bit for bit (counter-based RNG + per-pixel
     in-order accumulation make the result independent of which lane traces which path when)"""
     imgs = {}
-    for v in (1, 4, 5, 0):
+    for v in (1, 4, 5, 6, 7, 0):
         with pt.Pathtracer(320, 180) as P:
             cam = P.loadSceneFile(f"{pt.ASSETS}/scenes/generated_scene.json", cwd=pt.ASSETS)
             P.setOption("variant", v)
