@@ -1,11 +1,16 @@
 // trace_common.cuh — pieces shared by the trace kernels (trace_kernels.cu, trace_wavefront.cu).
 #pragma once
+#define PTB_PRIM_FN __device__ __noinline__ // one out-of-line primitive test per kernel (code size, see trace_device.cuh)
 #include "trace_device.cuh"
 
 namespace ptb
 {
 
 constexpr int kThreads = 256;
+
+// one out-of-line copy each of the bilinear texture tap and of Philox: both are used by two stages of every trace kernel
+static __device__ __noinline__ V3 texLookupNI(const TexDesc *textures, uint32_t handle, float u, float v) { return texLookup(textures, handle, u, v); }
+static __device__ __noinline__ uint4 philoxNI(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1) { return philox4x32_10(c0, c1, c2, 0u, k0, k1); }
 constexpr uint32_t kInvalid = 0xffffffffu;
 
 // ---------------------------------------------------------------------------------------------------------------

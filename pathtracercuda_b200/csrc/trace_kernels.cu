@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kThreads, 3) traceKernel(const RenderParams p)
 			if (!alive)
 			{
 				sampleIdx = p.sampleOffset + sample * p.sampleStride;
-				const uint4 r = philox4x32_10(pixel, sampleIdx, 0u, 0u, p.seedLo, p.seedHi);
+				const uint4 r = philoxNI(pixel, sampleIdx, 0u, p.seedLo, p.seedHi);
 				const uint32_t px = pixel % p.width, py = pixel / p.width;
 				const float u = divExact(float(px) + uniform01(r.x), float(p.width)); // trace.cu:190
 				const float v = divExact(float(py) + uniform01(r.y), float(p.height));
@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(kThreads, 3) traceKernel(const RenderParams p)
 				if (COUNT) ++misses;
 				if (p.scene.skybox != 0)
 				{
-					const float theta = acosf(rd.y), phi = atan2f(rd.z, rd.x);
-					const V3 sky = texLookup(p.scene.textures, p.scene.skybox, phi / (2.0f * PT_PI), theta / PT_PI);
+					const float theta = fastAcos(rd.y), phi = fastAtan2(rd.z, rd.x);
+					const V3 sky = texLookupNI(p.scene.textures, p.scene.skybox, phi / (2.0f * PT_PI), theta / PT_PI);
 					L = L + thr * sky;
 				}
 				terminate = true;
@@ -136,14 +136,14 @@ __global__ void __launch_bounds__(kThreads, 3) traceKernel(const RenderParams p)
 				const uint32_t tex = __float_as_uint(m2.x), mtype = __float_as_uint(m2.y);
 				if (tex != 0 && tex <= p.scene.texCount)
 				{
-					const V3 tap = texLookup(p.scene.textures, tex, s.u, s.v); // Material.inl:26-35
+					const V3 tap = texLookupNI(p.scene.textures, tex, s.u, s.v); // Material.inl:26-35
 					base = mk(fastPow(tap.x, 2.2f), fastPow(tap.y, 2.2f), fastPow(tap.z, 2.2f));
 				}
 				float rnd0, rnd1;
 				if (bounce == 0) { rnd0 = uniform01(rz); rnd1 = uniform01(rw); }
 				else if (bounce & 1u)
 				{
-					const uint4 r = philox4x32_10(pixel, sampleIdx, (bounce + 1u) >> 1, 0u, p.seedLo, p.seedHi);
+					const uint4 r = philoxNI(pixel, sampleIdx, (bounce + 1u) >> 1, p.seedLo, p.seedHi);
 					rnd0 = uniform01(r.x); rnd1 = uniform01(r.y);
 					rz = r.z; rw = r.w;
 				}

@@ -59,10 +59,6 @@ __device__ __noinline__ PoolBest poolFoldPrim(const float4 *prims, uint32_t prim
 	return best;
 }
 
-// one out-of-line copy each of the bilinear texture tap and of Philox (both are used by two stages)
-__device__ __noinline__ V3 poolTexLookup(const TexDesc *textures, uint32_t handle, float u, float v) { return texLookup(textures, handle, u, v); }
-__device__ __noinline__ uint4 poolPhilox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1) { return philox4x32_10(c0, c1, c2, 0u, k0, k1); }
-
 template <bool SMEM, bool COUNT>
 __global__ void __launch_bounds__(kPoolThreads, 1) traceKernelWP(const RenderParams p, const uint32_t sceneBytesAligned, const int traceLow, const int nodeLow)
 {
@@ -239,7 +235,7 @@ __global__ void __launch_bounds__(kPoolThreads, 1) traceKernelWP(const RenderPar
 				const uint32_t tex = __float_as_uint(m2.x), mtype = __float_as_uint(m2.y);
 				if (tex != 0 && tex <= p.scene.texCount)
 				{
-					const V3 tap = poolTexLookup(p.scene.textures, tex, sf.u, sf.v); // Material.inl:26-35
+					const V3 tap = texLookupNI(p.scene.textures, tex, sf.u, sf.v); // Material.inl:26-35
 					base = mk(fastPow(tap.x, 2.2f), fastPow(tap.y, 2.2f), fastPow(tap.z, 2.2f));
 				}
 				const uint32_t state = PU(F_STATE, s);
@@ -247,7 +243,7 @@ __global__ void __launch_bounds__(kPoolThreads, 1) traceKernelWP(const RenderPar
 				float rnd0, rnd1;
 				if (bounce != 0u && (bounce & 1u))
 				{
-					const uint4 r = poolPhilox(PU(F_PIXEL, s), p.sampleOffset + (state & kStateSampleMask) * p.sampleStride, (bounce + 1u) >> 1, p.seedLo, p.seedHi);
+					const uint4 r = philoxNI(PU(F_PIXEL, s), p.sampleOffset + (state & kStateSampleMask) * p.sampleStride, (bounce + 1u) >> 1, p.seedLo, p.seedHi);
 					rnd0 = uniform01(r.x); rnd1 = uniform01(r.y);
 					PU(F_RZ, s) = r.z; PU(F_RW, s) = r.w;
 				}
@@ -303,8 +299,8 @@ __global__ void __launch_bounds__(kPoolThreads, 1) traceKernelWP(const RenderPar
 						if (p.scene.skybox != 0)
 						{
 							const V3 mrd = mk(PF(F_DX, s), PF(F_DY, s), PF(F_DZ, s)), thr = mk(PF(F_TX, s), PF(F_TY, s), PF(F_TZ, s));
-							const float theta = acosf(mrd.y), phi = atan2f(mrd.z, mrd.x);
-							const V3 sky = poolTexLookup(p.scene.textures, p.scene.skybox, phi / (2.0f * PT_PI), theta / PT_PI);
+							const float theta = fastAcos(mrd.y), phi = fastAtan2(mrd.z, mrd.x);
+							const V3 sky = texLookupNI(p.scene.textures, p.scene.skybox, phi / (2.0f * PT_PI), theta / PT_PI);
 							L = L + thr * sky;
 						}
 					}
@@ -341,7 +337,7 @@ __global__ void __launch_bounds__(kPoolThreads, 1) traceKernelWP(const RenderPar
 			if (alive)
 			{
 				const uint32_t sampleIdx = p.sampleOffset + sample * p.sampleStride;
-				const uint4 r = poolPhilox(pixel, sampleIdx, 0u, p.seedLo, p.seedHi);
+				const uint4 r = philoxNI(pixel, sampleIdx, 0u, p.seedLo, p.seedHi);
 				const uint32_t px = pixel % p.width, py = pixel / p.width;
 				const float u = divExact(float(px) + uniform01(r.x), float(p.width)); // trace.cu:190
 				const float v = divExact(float(py) + uniform01(r.y), float(p.height));
