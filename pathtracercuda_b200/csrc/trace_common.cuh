@@ -8,6 +8,19 @@ namespace ptb
 
 constexpr int kThreads = 256;
 
+// pixel index -> (x, y) without an integer division (exact while the index is exact in fp32; one correction step)
+__device__ __forceinline__ void pixelToXY(uint32_t pixel, uint32_t width, uint32_t height, uint32_t &px, uint32_t &py)
+{
+	if (width * height <= (1u << 24))
+	{
+		py = __float2uint_rz(__fdividef(__uint2float_rn(pixel) + 0.5f, __uint2float_rn(width)));
+		px = pixel - py * width;
+		if (int(px) < 0) { --py; px += width; }
+		else if (px >= width) { ++py; px -= width; }
+	}
+	else { px = pixel % width; py = pixel / width; }
+}
+
 // one out-of-line copy each of the bilinear texture tap and of Philox: both are used by two stages of every trace kernel
 static __device__ __noinline__ V3 texLookupNI(const TexDesc *textures, uint32_t handle, float u, float v) { return texLookup(textures, handle, u, v); }
 static __device__ __noinline__ uint4 philoxNI(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1) { return philox4x32_10(c0, c1, c2, 0u, k0, k1); }

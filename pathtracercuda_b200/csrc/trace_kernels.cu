@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(kThreads, 3) traceKernel(const RenderParams p)
 			{
 				sampleIdx = p.sampleOffset + sample * p.sampleStride;
 				const uint4 r = philoxNI(pixel, sampleIdx, 0u, p.seedLo, p.seedHi);
-				const uint32_t px = pixel % p.width, py = pixel / p.width;
+				uint32_t px, py;
+				pixelToXY(pixel, p.width, p.height, px, py);
 				const float u = divExact(float(px) + uniform01(r.x), float(p.width)); // trace.cu:190
 				const float v = divExact(float(py) + uniform01(r.y), float(p.height));
 				rz = r.z; rw = r.w;
@@ -295,8 +296,8 @@ int launchTrace(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t str
 	switch (cfg.variant)
 	{
 	case 1: return PT_PICK(traceKernel, , 0);      // per-lane if/else traversal
-	case 4: return PT_PICK(traceKernel, , 1);      // while-while traversal
-	default: return PT_PICK(traceKernel, , 2);     // 5: while-while + speculative leaf parking
+	case 5: return PT_PICK(traceKernel, , 2);      // while-while + speculative leaf parking
+	default: return PT_PICK(traceKernel, , 1);     // 0 / 4: while-while traversal (fastest measured)
 	}
 #undef PT_PICK
 }

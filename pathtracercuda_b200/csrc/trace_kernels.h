@@ -38,7 +38,7 @@ struct LaunchConfig
 	int smCount = 148;
 	int smemScene = 1;   // stage the scene in shared memory when it fits
 	int countWork = 0;   // node/prim/shade/miss counters
-	int variant = 0;     // kernel variant (0 = default = 5: persistent per-lane kernel, while-while + leaf parking; 1/4: its simpler traversals;
+	int variant = 0;     // kernel variant (0 = default = 4: persistent per-lane kernel, while-while traversal; 1: if/else traversal, 5: + leaf parking;
 	                     //  6: warp-pool wavefront, 7: CTA-pool warp-specialised wavefront - both measured slower)
 	int traceLow = 0;    // warp-pool: run shade/generate early when fewer than this many lanes could traverse (0 = 24)
 	int nodeLow = 0;     // warp-pool: the node loop leaves when fewer than this many lanes are still walking (0 = 24)

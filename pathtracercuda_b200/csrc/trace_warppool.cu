@@ -338,7 +338,8 @@ __global__ void __launch_bounds__(kPoolThreads, 1) traceKernelWP(const RenderPar
 			{
 				const uint32_t sampleIdx = p.sampleOffset + sample * p.sampleStride;
 				const uint4 r = philoxNI(pixel, sampleIdx, 0u, p.seedLo, p.seedHi);
-				const uint32_t px = pixel % p.width, py = pixel / p.width;
+				uint32_t px, py;
+				pixelToXY(pixel, p.width, p.height, px, py);
 				const float u = divExact(float(px) + uniform01(r.x), float(p.width)); // trace.cu:190
 				const float v = divExact(float(py) + uniform01(r.y), float(p.height));
 				const V3 d = cameraDir(p.cam, u, v);
