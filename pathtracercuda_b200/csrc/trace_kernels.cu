@@ -26,7 +26,7 @@ namespace ptb
 // the trace kernel
 // ---------------------------------------------------------------------------------------------------------------
 template <bool SMEM, bool COUNT, int TRAV>
-__global__ void __launch_bounds__(kThreads, 3) traceKernel(const RenderParams p)
+__global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderParams p)
 {
 	extern __shared__ __align__(128) float4 smemScene[];
 	__shared__ uint64_t mbar;
@@ -266,10 +266,10 @@ static int launchKernel(K kern, const RenderParams &p, const LaunchConfig &cfg, 
 {
 	if (smemBytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemBytes));
 	int blocksPerSm = 0;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, kern, kThreads, smemBytes);
+	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, kern, kTraceThreads, smemBytes);
 	if (blocksPerSm < 1) blocksPerSm = 1;
 	const int grid = cfg.smCount * blocksPerSm;
-	kern<<<grid, kThreads, smemBytes, stream>>>(p);
+	kern<<<grid, kTraceThreads, smemBytes, stream>>>(p);
 	return 1;
 }
 
