@@ -127,7 +127,10 @@ const float *pt_get_hdr_mean(pt_context *ctx);
  *                    (k=8 reproduces the reference headless CLI, main.cpp:271-278); 0: one frame per call
  *  "count_work"      1: count node visits / primitive tests / shades / misses (slower)
  *  "smem_scene"      0: never stage the scene in shared memory; 1: auto (default)
- *  "max_bounces"     path segments, default 5 (kernels/trace.cu:109) */
+ *  "max_bounces"     path segments, default 5 (kernels/trace.cu:109)
+ *  "max_leaf"        primitives per BVH leaf at most (default 4, the reference's Pathtracer.cpp:121; set before the scene)
+ *  "max_global"      how many scene-spanning primitives are hoisted out of the BVH (default 8; set before the scene)
+ *  "variant"         trace kernel variant, 0 = default (see csrc/trace_kernels.h LaunchConfig) */
 int pt_set_option(pt_context *ctx, const char *key, double value);
 int pt_get_stats(const pt_context *ctx, pt_stats *out);
 

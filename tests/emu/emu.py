@@ -60,6 +60,14 @@ class Emu:
         self.L.emu_scene_arrays(self.s, _p(nd), _p(pr))
         return nd, pr
 
+    def fast_angles(self, y, x):
+        y = np.ascontiguousarray(y, np.float32)
+        x = np.ascontiguousarray(x, np.float32)
+        a, c = np.zeros_like(y), np.zeros_like(y)
+        self.L.emu_fast_angles.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        self.L.emu_fast_angles(y.size, _p(y), _p(x), _p(a), _p(c))
+        return a, c
+
     def global_count(self):
         self.L.emu_global_count.restype = C.c_uint32
         self.L.emu_global_count.argtypes = [C.c_void_p]

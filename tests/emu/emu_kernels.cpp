@@ -223,6 +223,11 @@ uint64_t emu_render(void *p, const pt_camera_desc *cd, uint32_t width, uint32_t 
 	g_lastWork[0] = nvTot; g_lastWork[1] = ptTot;
 	return raysTot;
 }
+// the compact atan2 / acos used for the equirectangular lookups (accuracy test)
+void emu_fast_angles(size_t n, const float *y, const float *x, float *atan2Out, float *acosOut)
+{
+	for (size_t i = 0; i < n; ++i) { atan2Out[i] = fastAtan2(y[i], x[i]); acosOut[i] = fastAcos(x[i]); }
+}
 // node visits / primitive tests of the last emu_render (BVH quality experiments)
 void emu_last_work(uint64_t *out) { out[0] = g_lastWork[0]; out[1] = g_lastWork[1]; }
 }

@@ -70,3 +70,24 @@ def test_quirks_match_oracle():
     ie, te, ne = E.trace_rays(o, d)
     assert io[0] == 0 and to[0] == np.float32(0.001)
     assert np.array_equal(io, ie) and np.allclose(to, te, rtol=1e-6) and np.allclose(no, ne, atol=1e-6)
+
+
+def test_compact_atan2_acos_accuracy():
+    """the equirectangular lookups use a compact atan2 / acos (trace_device.cuh fastAtan2): far below the 1/256-texel
+    resolution of the texture unit the reference samples with (2e-7 rad is 1e-4 texel of a 4096-wide map)"""
+    E = Emu([pt.make_object("SPHERE")], 4)
+    rng = np.random.default_rng(7)
+    v = rng.normal(size=(200000, 2)).astype(np.float32)
+    v = np.concatenate([v, [[0, 1], [0, -1], [1, 0], [-1, 0], [1e-20, 1], [1, 1e-20], [-1e-20, -1], [3, -3]]]).astype(np.float32)
+    a, _ = E.fast_angles(v[:, 0], v[:, 1])
+    ref = np.arctan2(v[:, 0].astype(np.float64), v[:, 1].astype(np.float64))
+    err = np.abs(a - ref)
+    err = np.minimum(err, 2 * np.pi - err)      # +pi and -pi are the same direction
+    assert err.max() < 4e-7, err.max()
+    c = np.clip(rng.uniform(-1, 1, 200000), -1, 1).astype(np.float32)
+    c = np.concatenate([c, [-1, 1, 0, 0.9999999, -0.9999999]]).astype(np.float32)
+    _, ac = E.fast_angles(np.zeros_like(c), c)
+    # near |c| = 1 acos is ill-conditioned in fp32 (the library routine has the same sqrt(1 - c^2) sensitivity)
+    assert np.abs(ac - np.arccos(c.astype(np.float64))).max() < 4e-4
+    mid = np.abs(c) < 0.99
+    assert np.abs(ac - np.arccos(c.astype(np.float64)))[mid].max() < 1e-6
