@@ -37,6 +37,7 @@ constexpr int kStackSize = 48;
 // tested first by every ray: the whole warp runs the same test on the same record (no divergence, broadcast loads), the
 // traversal starts with a tight t_max, and the tree is not polluted by boxes that overlap everything.
 constexpr uint32_t kMaxGlobalPrims = 8;
+constexpr size_t kTopOrderNodes = 4096; // nodes[0..4096) are numbered breadth-first, the rest depth-first (scene_compile.cpp)
 constexpr float kGlobalAreaFraction = 0.25f;
 
 // One primitive = world->local 3x4 (the reference's Hittable rows, Hittable.h:22-24) + shape type + indices (64 B).

@@ -365,6 +365,49 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 		return false;
 	}
 	out.nodes.resize(b.nextNode.load());
+	// Renumber the nodes: the first kTopOrderNodes in BREADTH-FIRST order (the levels every ray walks sit in a few
+	// consecutive cache lines), the rest depth-first (subtrees contiguous).  Also makes the layout independent of the
+	// order in which the parallel build tasks ran.  (Staging that breadth-first prefix in shared memory for scenes that do
+	// not fit was measured and dropped: L1 already holds it, and the generic-address loads cost more - 7.2 vs 7.8 Grays/s.)
+	if (out.nodes.size() > 1)
+	{
+		const size_t n = out.nodes.size();
+		std::vector<int32_t> newIndex(n, -1), order;
+		order.reserve(n);
+		std::vector<int32_t> queue;
+		queue.push_back(0);
+		size_t head = 0;
+		while (head < queue.size() && order.size() < kTopOrderNodes)
+		{
+			const int32_t i = queue[head++];
+			newIndex[i] = int32_t(order.size());
+			order.push_back(i);
+			for (int c = 0; c < 2; ++c)
+				if (out.nodes[i].child[c] >= 0) queue.push_back(out.nodes[i].child[c]);
+		}
+		// the frontier (queued but not numbered) and everything below it: depth-first, in queue order
+		std::vector<int32_t> stack;
+		for (size_t q = queue.size(); q-- > head;) stack.push_back(queue[q]);
+		while (!stack.empty())
+		{
+			const int32_t i = stack.back();
+			stack.pop_back();
+			newIndex[i] = int32_t(order.size());
+			order.push_back(i);
+			for (int c = 1; c >= 0; --c)
+				if (out.nodes[i].child[c] >= 0) stack.push_back(out.nodes[i].child[c]);
+		}
+		if (order.size() != n) { err = "internal: BVH renumbering lost nodes"; return false; }
+		std::vector<Node> renum(n);
+		for (size_t k = 0; k < n; ++k)
+		{
+			Node nd = out.nodes[order[k]];
+			for (int c = 0; c < 2; ++c)
+				if (nd.child[c] >= 0) nd.child[c] = newIndex[nd.child[c]];
+			renum[k] = nd;
+		}
+		out.nodes.swap(renum);
+	}
 	// min/max -> centre / half extent, padded outwards: the traversal computes t_c = c*inv - o*inv in fp32, so the box
 	// must absorb a few ulp of |c|, of its own size and of the scene scale (ray origins) to stay conservative
 	{
