@@ -32,8 +32,30 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SCENE = "generated_scene"
+SCENE = "generated_scene"   # --scene: cornell_box | generated_scene | synthetic_<N> (BASELINE.json configs 2-4)
 W, H = 1920, 1080
+SCENE_DIR = None            # directory holding <SCENE>.json and the assets it names (set by resolve_scene)
+
+
+def resolve_scene(args):
+    """bundled scenes live under assets/scenes; synthetic_<N> is generated into a temporary directory (seed 1984)"""
+    global SCENE, W, H, SCENE_DIR
+    import pathtracercuda_b200 as pt
+    SCENE, W, H = args.scene, args.width, args.height
+    if SCENE.startswith("synthetic_"):
+        import tempfile
+        from pathtracercuda_b200 import scenegen
+        SCENE_DIR = tempfile.mkdtemp(prefix="ptb_scene_")
+        os.symlink(pt.ASSETS + "/skybox.hdr", SCENE_DIR + "/skybox.hdr")
+        scenegen.write_synthetic_scene(f"{SCENE_DIR}/{SCENE}.json", int(SCENE.split("_")[1]))
+        return f"{SCENE_DIR}/{SCENE}.json", SCENE_DIR
+    SCENE_DIR = pt.ASSETS + "/scenes"
+    return f"{SCENE_DIR}/{SCENE}.json", pt.ASSETS
+
+
+def workload_label(spp):
+    cfg = {"generated_scene": "BASELINE.json config 3", "cornell_box": "BASELINE.json config 2"}.get(SCENE, "BASELINE.json config 4")
+    return f"{SCENE}.json {W}x{H} {spp} spp ({cfg}), stand-in earth.png/skybox.hdr (reference assets not in its checkout)"
 
 # algorithmic FP32 operations per unit of work, counted from the reference source (SURVEY.md §8d table)
 OPS_NODE_BOX = 24.0          # one ray/box slab test (AABB.inl:22-44); a two-box node visit = 2 of these
@@ -70,21 +92,24 @@ def cpu_baseline(seconds=12.0):
     from oracle import imgio, orc
     cores = os.cpu_count() or 1
     w, h = 480, 270
-    objs, tex, sky, cam = pt.parse_scene_py(f"{pt.ASSETS}/scenes/{SCENE}.json", w, h)
+    objs, tex, sky, cam = pt.parse_scene_py(f"{SCENE_DIR}/{SCENE}.json", w, h)
     skyimg = imgio.read_hdr(pt.ASSETS + "/skybox.hdr")
+    has_sky = bool(sky) and tex[sky - 1] == "skybox.hdr"  # cornell_box names a file that does not exist: black environment
     if orc.have_ref_host():
         R = orc.RefHost()
         for o in objs:
             o.material.texture = 0
         R.set_scene(objs)
         R.set_camera(cam)
-        R.set_sky(skyimg)
+        if has_sky:
+            R.set_sky(skyimg)
         run = lambda spp: R.render(w, h, spp)[1]
         kind = "reference"
     else:
         O = orc.Oracle(objs)
         O.add_texture(imgio.read_png(pt.ASSETS + "/earth.png"))
-        O.set_skybox(O.add_texture(skyimg))
+        if has_sky:
+            O.set_skybox(O.add_texture(skyimg))
         run = lambda spp: O.render(cam, w, h, spp)[1]
         kind = "port"
     t0 = time.perf_counter()
@@ -106,9 +131,10 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    scene_path, scene_cwd = resolve_scene(args)
     line = {"impl": "reference", "metric": "Mrays/s", "unit": "Mrays/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{SCENE}.json {W}x{H} {args.spp} spp (BASELINE.json config 3), stand-in earth.png/skybox.hdr", "spp": args.spp,
+            "config": {"workload": workload_label(args.spp), "spp": args.spp,
                        "l2": "not flushed: the reference re-launches its kernel every 8 spp, working set 56 KB scene + 133 MB state"}}
     cb = cpu_baseline()
     if not os.path.exists(orc.REF_PT):
@@ -117,7 +143,7 @@ def run_reference(args):
                      "e2e": {"value": cb["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
         print(json.dumps(line))
         return 0
-    objs, tex, sky, cam = pt.parse_scene_py(f"{pt.ASSETS}/scenes/{SCENE}.json", W, H)
+    objs, tex, sky, cam = pt.parse_scene_py(scene_path, W, H)
     import tempfile
     with tempfile.TemporaryDirectory() as td:
         cnt = orc.ref_gpu_count(objs, cam, W, H, 32, td)  # the reference's own rays per sample (its seeds, its slicing)
@@ -125,7 +151,7 @@ def run_reference(args):
     times, walls = [], []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
-        p = subprocess.run([orc.REF_PT, "-w", str(W), "-h", str(H), "-spp", str(args.spp), f"scenes/{SCENE}.json"], cwd=pt.ASSETS, capture_output=True, text=True)
+        p = subprocess.run([orc.REF_PT, "-w", str(W), "-h", str(H), "-spp", str(args.spp), os.path.relpath(scene_path, scene_cwd)], cwd=scene_cwd, capture_output=True, text=True)
         wall = time.perf_counter() - t0
         ms = [float(l.split(" in ")[1].split(" ms")[0]) for l in p.stdout.splitlines() if l.startswith("Finished accumulating")]
         if p.returncode != 0 or not ms:
@@ -154,6 +180,9 @@ def main():
     ap.add_argument("--spp", type=int, default=4096)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--scene", default="generated_scene")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -175,9 +204,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE {world}"
 
-    path = f"{pt.ASSETS}/scenes/{SCENE}.json"
+    path, scene_cwd = resolve_scene(args)
     P = pt.Pathtracer(W, H, device=local)
-    cam = P.loadSceneFile(path, cwd=pt.ASSETS)
+    cam = P.loadSceneFile(path, cwd=scene_cwd)
     P.setOption("variant", args.variant)
     accum = attach_torch_accumulator(P, torch.device("cuda", local))
     off, stride, count = partition_samples(args.spp, rank, world)
@@ -290,9 +319,9 @@ def main():
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{SCENE}.json {W}x{H} {args.spp} spp (BASELINE.json config 3), stand-in earth.png/skybox.hdr (reference assets not in its checkout)",
+            "config": {"workload": workload_label(args.spp),
                        "spp": args.spp, "spp_per_gpu": count, "parallelism": f"sample-partitioned x{world} + 1 NCCL reduce" if world > 1 else "single GPU",
-                       "l2": "flushed between steps (256 MiB memset); scene (64 KB) is staged in shared memory, output 33 MB accumulation buffer",
+                       "l2": f"flushed between steps (256 MiB memset); scene ({st0.scene_bytes / 1e3:.0f} KB) " + ("is staged in shared memory" if st0.scene_in_smem else "is read through L1/L2") + f", output {W * H * 16 / 1e6:.0f} MB accumulation buffer",
                        "kernel_variant": args.variant},
             "samples_per_s": W * H * args.spp / ms_step * 1e3, "samples_per_s_per_gpu": W * H * args.spp / ms_step * 1e3 / world, "rays_per_sample": rays_step / (W * H * args.spp),
             "wall_ms_per_step": wall / args.steps * 1e3,
