@@ -106,9 +106,51 @@ struct Parser
 			if (i >= n || s[i] < '0' || s[i] > '9') return fail("bad exponent");
 			while (i < n && s[i] >= '0' && s[i] <= '9') ++i;
 		}
-		std::string tok(s + b, i - b);
 		v.kind = isFloat ? JsonValue::Float : JsonValue::Int;
-		v.num = strtod(tok.c_str(), nullptr);
+		// Clinger's fast path: a decimal with <= 15 significant digits and a power of ten up to 10^22 is ONE correctly
+		// rounded double operation (both operands exact); everything else goes to strtod
+		{
+			size_t k = b;
+			const bool neg = s[k] == '-';
+			if (neg) ++k;
+			unsigned long long mant = 0;
+			int digits = 0, exp10 = 0;
+			bool fast = true;
+			for (; k < i && s[k] >= '0' && s[k] <= '9'; ++k) { mant = mant * 10 + unsigned(s[k] - '0'); if (mant) ++digits; }
+			if (k < i && s[k] == '.')
+				for (++k; k < i && s[k] >= '0' && s[k] <= '9'; ++k) { mant = mant * 10 + unsigned(s[k] - '0'); if (mant) ++digits; --exp10; }
+			if (digits > 15) fast = false;
+			if (fast && k < i && (s[k] == 'e' || s[k] == 'E'))
+			{
+				++k;
+				bool eneg = false;
+				if (s[k] == '+' || s[k] == '-') { eneg = s[k] == '-'; ++k; }
+				int e = 0;
+				for (; k < i && e < 10000; ++k) e = e * 10 + (s[k] - '0');
+				exp10 += eneg ? -e : e;
+			}
+			static const double p10[] = { 1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22 };
+			if (fast && exp10 >= -22 && exp10 <= 22)
+			{
+				double d = double(mant);
+				d = exp10 < 0 ? d / p10[-exp10] : d * p10[exp10];
+				v.num = neg ? -d : d;
+				return true;
+			}
+		}
+		char buf[64];
+		const size_t len = i - b;
+		if (len < sizeof buf)
+		{
+			memcpy(buf, s + b, len);
+			buf[len] = 0;
+			v.num = strtod(buf, nullptr);
+		}
+		else
+		{
+			std::string tok(s + b, len);
+			v.num = strtod(tok.c_str(), nullptr);
+		}
 		return true;
 	}
 	bool value(JsonValue &v)
@@ -121,6 +163,7 @@ struct Parser
 		if (c == '{')
 		{
 			v.kind = JsonValue::Object;
+			v.obj.reserve(8);
 			++i;
 			ws();
 			if (i < n && s[i] == '}') { ++i; }
@@ -136,7 +179,10 @@ struct Parser
 					++i;
 					JsonValue child;
 					if (!value(child)) { ok = false; break; }
-					v.obj[key] = std::move(child);
+					bool replaced = false;
+					for (auto &kv : v.obj)
+						if (kv.first == key) { kv.second = std::move(child); replaced = true; break; }
+					if (!replaced) v.obj.emplace_back(std::move(key), std::move(child));
 					ws();
 					if (i < n && s[i] == ',') { ++i; continue; }
 					if (i < n && s[i] == '}') { ++i; break; }
@@ -147,6 +193,7 @@ struct Parser
 		else if (c == '[')
 		{
 			v.kind = JsonValue::Array;
+			v.arr.reserve(4);
 			++i;
 			ws();
 			if (i < n && s[i] == ']') { ++i; }

@@ -2,7 +2,6 @@
 // the reference's loader depends on: whether a number was written as a float literal ('.', 'e' or 'E' present) or an
 // integer literal (nlohmann's is_number_float(), used by reference SceneLoader.cpp:163-171 — quirk Q5).
 #pragma once
-#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -16,14 +15,15 @@ struct JsonValue
 	double num = 0.0;
 	std::string str;
 	std::vector<JsonValue> arr;
-	std::map<std::string, JsonValue> obj;
+	std::vector<std::pair<std::string, JsonValue>> obj; // insertion order; a repeated key replaces the earlier value (as nlohmann)
 
 	bool isNumber() const { return kind == Int || kind == Float; }
 	const JsonValue *find(const char *key) const
 	{
 		if (kind != Object) return nullptr;
-		auto it = obj.find(key);
-		return it == obj.end() ? nullptr : &it->second;
+		for (const auto &kv : obj)
+			if (kv.first == key) return &kv.second;
+		return nullptr;
 	}
 };
 
