@@ -266,6 +266,7 @@ int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ign
 		p.seedLo = uint32_t(c->seed);
 		p.seedHi = uint32_t(c->seed >> 32);
 		p.maxBounces = c->maxBounces;
+		p.regenLow = c->launch.regenLow > 0 ? uint32_t(c->launch.regenLow) : 8u;
 		launches = launchTrace(p, c->launch, c->stream, &usedSmem);
 	}
 	CK(cudaEventRecord(c->evStop, c->stream));
@@ -360,6 +361,7 @@ int pt_set_option(pt_context *c, const char *key, double value)
 	else if (k == "pool_warps") c->launch.poolWarps = int(value);
 	else if (k == "trace_warps") c->launch.traceWarps = int(value);
 	else if (k == "ready_low") c->launch.readyLow = int(value);
+	else if (k == "regen_low") c->launch.regenLow = int(value);
 	else if (k == "pool_slots") c->launch.poolSlots = int(value);
 	else return setError(PT_E_INVALID, "pt_set_option: unknown option " + k);
 	return PT_OK;

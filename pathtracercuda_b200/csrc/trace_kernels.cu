@@ -25,7 +25,7 @@ namespace ptb
 // ---------------------------------------------------------------------------------------------------------------
 // the trace kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <bool SMEM, bool COUNT, int TRAV>
+template <bool SMEM, bool COUNT, int TRAV, bool SHARE>
 __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderParams p)
 {
 	extern __shared__ __align__(128) float4 smemScene[];
@@ -55,9 +55,64 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 	V3 ro = camO, rd = mk(0.0f, 0.0f, 1.0f), thr = mk(1.0f, 1.0f, 1.0f), L = mk(0.0f, 0.0f, 0.0f);
 	uint32_t bounce = 0, rz = 0, rw = 0, sampleIdx = 0;
 	uint32_t rays = 0, nodeVisits = 0, primTests = 0, shades = 0, misses = 0;
+	uint32_t wNext = p.spp; // SHARE: next sample of the warp's pixel to hand out (warp-uniform)
 
 	while (true)
 	{
+		bool generate;
+		if constexpr (SHARE)
+		{
+			// ---- the 32 lanes of the warp work on the SAME pixel: a lane without a path takes the pixel's next sample.
+			// Camera rays of one warp are then (nearly) the same ray, the first hits the same primitive, the scattered rays
+			// start from the same place: coherent node fetches (shared-memory broadcast) and fewer divergent branches ----
+			generate = false;
+			const uint32_t needMask = __ballot_sync(0xffffffffu, !alive);
+			if (needMask)
+			{
+				// hand out new samples only to groups of >= regenLow idle lanes (or when nobody is left tracing): the camera
+				// rays of one group are nearly the same ray and stay in step through their first hit
+				if (pixel != kInvalid && wNext < p.spp && (uint32_t(__popc(needMask)) >= p.regenLow || needMask == 0xffffffffu || p.spp - wNext < 32u))
+				{
+					const uint32_t mine = wNext + __popc(needMask & ((1u << lane) - 1u));
+					if (!alive && mine < p.spp) { sample = mine; generate = true; }
+					wNext = min(p.spp, wNext + uint32_t(__popc(needMask)));
+				}
+				if (!__any_sync(0xffffffffu, alive || generate))
+				{
+					// the pixel is complete: add the lanes' partial sums in a fixed order (butterfly), one lane writes
+					if (pixel != kInvalid)
+					{
+#pragma unroll
+						for (int o = 16; o > 0; o >>= 1)
+						{
+							color.x += __shfl_xor_sync(0xffffffffu, color.x, o);
+							color.y += __shfl_xor_sync(0xffffffffu, color.y, o);
+							color.z += __shfl_xor_sync(0xffffffffu, color.z, o);
+						}
+						if (lane == 0)
+						{
+							float4 out = make_float4(color.x, color.y, color.z, 1.0f); // trace.cu:196-198
+							if (!p.ignoreHistory)
+							{
+								const float4 prev = p.accum[pixel];
+								out.x += prev.x; out.y += prev.y; out.z += prev.z;
+							}
+							p.accum[pixel] = out;
+						}
+					}
+					color = mk(0.0f, 0.0f, 0.0f);
+					unsigned long long next = 0;
+					if (lane == 0) next = atomicAdd(&p.counters[kCtrWork], 1ull);
+					next = __shfl_sync(0xffffffffu, next, 0);
+					if (next >= totalPixels) break;
+					pixel = uint32_t(next);
+					wNext = 0;
+					continue;
+				}
+			}
+		}
+		else
+		{
 		// ---- accumulate + fetch the next pixel (warp-aggregated atomic: ballot + popc prefix) ----
 		const bool need = active && !alive && sample == p.spp;
 		if (need && pixel != kInvalid)
@@ -85,11 +140,13 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 			}
 		}
 		if (!__any_sync(0xffffffffu, active)) break;
+		generate = active && !alive;
+		}
 
-		if (active)
+		if (SHARE ? (alive || generate) : active)
 		{
 			// ---- generate (trace.cu:187-192) ----
-			if (!alive)
+			if (generate)
 			{
 				sampleIdx = p.sampleOffset + sample * p.sampleStride;
 				const uint4 r = philoxNI(pixel, sampleIdx, 0u, p.seedLo, p.seedHi);
@@ -293,11 +350,18 @@ int launchTrace(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t str
 #define PT_PICK(KERN, ...)                                                                                                        \
 	(smem ? (cfg.countWork ? launchKernel(KERN<true, true __VA_ARGS__>, p, cfg, sb, stream) : launchKernel(KERN<true, false __VA_ARGS__>, p, cfg, sb, stream)) \
 	      : (cfg.countWork ? launchKernel(KERN<false, true __VA_ARGS__>, p, cfg, sb, stream) : launchKernel(KERN<false, false __VA_ARGS__>, p, cfg, sb, stream)))
-	switch (cfg.variant)
+	// default: one pixel per warp for renders long enough to amortise the drain at the end of every pixel (the last paths of
+	// a pixel run with the other lanes idle: ~half a path per spp/32 samples), one pixel per lane otherwise
+	int variant = cfg.variant;
+	if (variant == 0) variant = p.spp >= 128 ? 8 : 4;
+	switch (variant)
 	{
-	case 1: return PT_PICK(traceKernel, , 0);      // per-lane if/else traversal
-	case 5: return PT_PICK(traceKernel, , 2);      // while-while + speculative leaf parking
-	default: return PT_PICK(traceKernel, , 1);     // 0 / 4: while-while traversal (fastest measured)
+	case 1: return PT_PICK(traceKernel, , 0, false);      // per-lane if/else traversal
+	case 5: return PT_PICK(traceKernel, , 2, false);      // while-while + speculative leaf parking
+	case 8: return PT_PICK(traceKernel, , 1, true);       // one pixel per WARP (lanes = samples), while-while
+	case 9: return PT_PICK(traceKernel, , 2, true);       // one pixel per warp, while-while + leaf parking
+	case 10: return PT_PICK(traceKernel, , 0, true);      // one pixel per warp, if/else traversal
+	default: return PT_PICK(traceKernel, , 1, false);     // 4: one pixel per lane, while-while traversal
 	}
 #undef PT_PICK
 }

@@ -31,6 +31,7 @@ struct RenderParams
 	uint32_t sampleOffset, sampleStride;
 	uint32_t seedLo, seedHi;
 	uint32_t maxBounces;
+	uint32_t regenLow = 1; // one-pixel-per-warp kernel: idle lanes wait until this many can start new samples together
 };
 
 struct LaunchConfig
@@ -38,13 +39,15 @@ struct LaunchConfig
 	int smCount = 148;
 	int smemScene = 1;   // stage the scene in shared memory when it fits
 	int countWork = 0;   // node/prim/shade/miss counters
-	int variant = 0;     // kernel variant (0 = default = 4: persistent per-lane kernel, while-while traversal; 1: if/else traversal, 5: + leaf parking;
+	int variant = 0;     // kernel variant (0 = default: 8 for spp >= 128, else 4.  4: one pixel per lane, while-while traversal; 1: if/else traversal;
+	                     //  5: + leaf parking; 8: one pixel per WARP (lanes = samples), while-while; 9/10: its other traversals;
 	                     //  6: warp-pool wavefront, 7: CTA-pool warp-specialised wavefront - both measured slower)
 	int traceLow = 0;    // warp-pool: run shade/generate early when fewer than this many lanes could traverse (0 = 24)
 	int nodeLow = 0;     // warp-pool: the node loop leaves when fewer than this many lanes are still walking (0 = 24)
 	int poolWarps = 0;   // warp-pool: warps per CTA (0 = as many as fit, <= 24)
 	int traceWarps = 0;  // wavefront: warps per CTA that only traverse (0 = half of them); the others run the other stages
 	int readyLow = -1;   // wavefront: stage warps run partial batches while the READY queue holds fewer rays than this (-1 = 128)
+	int regenLow = 0;    // see RenderParams::regenLow (0 = default)
 	int poolSlots = 0;   // CTA-pool wavefront: path slots per CTA (0 = 1280 with the scene in shared memory, 1536 without)
 	size_t maxSmemOptin = 0;
 };

@@ -152,18 +152,32 @@ def test_converged_image_within_reference_noise_floor(scene):
 
 
 def test_kernel_variants_bit_identical():
-    """every scheduling variant of the trace kernel computes the same image bit for bit (counter-based RNG + per-pixel
-    in-order accumulation make the result independent of which lane traces which path when)"""
-    imgs = {}
-    for v in (1, 4, 5, 6, 7, 0):
+    """every scheduling variant of the trace kernel computes the same image: bit for bit among the one-pixel-per-lane
+    kernels (counter-based RNG + per-pixel in-order accumulation make the result independent of which lane traces which
+    path when) and among the one-pixel-per-warp kernels (same paths, summed as 32 per-lane partial sums + a butterfly, so
+    only float reassociation separates the two families)"""
+    def run(v, spp, **opts):
         with pt.Pathtracer(320, 180) as P:
             cam = P.loadSceneFile(f"{pt.ASSETS}/scenes/generated_scene.json", cwd=pt.ASSETS)
             P.setOption("variant", v)
-            P.render(cam, 16, True)
-            P.render(cam, 16, False)
-            imgs[v] = P.getHDRMean()
+            for k, val in opts.items():
+                P.setOption(k, val)
+            P.render(cam, spp, True)
+            P.render(cam, spp, False)
+            return P.getHDRMean()
+    imgs = {v: run(v, 16) for v in (1, 4, 5, 6, 7, 0)}
     for v in imgs:
         assert np.array_equal(bits(imgs[1]), bits(imgs[v])), v
+    # one pixel per warp: 80 samples = two full rounds of 32 + a ragged one; deterministic run to run; the default for spp >= 128
+    lane = run(4, 80)
+    warp = [(v, run(v, 80)) for v in (8, 9, 10, 8)]
+    for v, img in warp:
+        assert np.array_equal(bits(warp[0][1]), bits(img)), v
+    assert np.allclose(warp[0][1], lane, rtol=2e-5, atol=1e-7)
+    assert np.allclose(run(8, 80, regen_low=1), lane, rtol=2e-5, atol=1e-7)
+    assert np.allclose(run(8, 80, regen_low=32), lane, rtol=2e-5, atol=1e-7)
+    assert np.array_equal(bits(run(0, 128)), bits(run(8, 128)))
+    assert np.allclose(run(8, 5), run(4, 5), rtol=2e-5, atol=1e-7)  # fewer samples than lanes
     with pt.Pathtracer(320, 180) as P:  # shared-memory scene vs global-memory scene
         cam = P.loadSceneFile(f"{pt.ASSETS}/scenes/generated_scene.json", cwd=pt.ASSETS)
         P.setOption("smem_scene", 0)
