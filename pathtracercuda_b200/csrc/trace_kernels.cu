@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t totalPixels = p.width * p.height;
+	const float invW = 1.0f / float(p.width), invH = 1.0f / float(p.height);
 	const V3 camO = mk(p.cam.origin[0], p.cam.origin[1], p.cam.origin[2]);
 
 	uint32_t pixel = kInvalid, sample = p.spp;
@@ -152,11 +153,11 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 				const uint4 r = philoxNI(pixel, sampleIdx, 0u, p.seedLo, p.seedHi);
 				uint32_t px, py;
 				pixelToXY(pixel, p.width, p.height, px, py);
-				const float u = divExact(float(px) + uniform01(r.x), float(p.width)); // trace.cu:190
-				const float v = divExact(float(py) + uniform01(r.y), float(p.height));
+				const float u = (float(px) + uniform01(r.x)) * invW; // trace.cu:190
+				const float v = (float(py) + uniform01(r.y)) * invH;
 				rz = r.z; rw = r.w;
 				ro = camO;
-				rd = cameraDir(p.cam, u, v);
+				rd = cameraDir<kHotExact>(p.cam, u, v);
 				thr = mk(1.0f, 1.0f, 1.0f);
 				L = mk(0.0f, 0.0f, 0.0f);
 				bounce = 0;
@@ -165,9 +166,23 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 
 			// ---- traverse + intersect (trace.cu:112) ----
 			++rays;
-			const Hit h = TRAV == 0 ? closestHit<SMEM, COUNT>(sv, ro, rd, 0.001f, nodeVisits, primTests)
-			              : TRAV == 1 ? closestHitWW<SMEM, COUNT, false>(sv, ro, rd, 0.001f, nodeVisits, primTests)
-			                          : closestHitWW<SMEM, COUNT, true>(sv, ro, rd, 0.001f, nodeVisits, primTests);
+			Hit h;
+			if constexpr (TRAV == 3)
+			{
+				// EXPERIMENT: camera rays traced twice (how much of the step is camera-ray traversal?)
+				const int reps = bounce == 0 ? 2 : 1;
+#pragma unroll 1
+				for (int rep = 0; rep < reps; ++rep)
+				{
+					V3 o2 = ro;
+					o2.x += float(rep) * 1e-30f;
+					h = closestHitWW<SMEM, COUNT, false, kHotExact>(sv, o2, rd, 0.001f, nodeVisits, primTests);
+				}
+			}
+			else
+			h = TRAV == 0 ? closestHit<SMEM, COUNT, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests)
+			              : TRAV == 1 ? closestHitWW<SMEM, COUNT, false, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests)
+			                          : closestHitWW<SMEM, COUNT, true, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests);
 
 			bool terminate;
 			if (h.prim < 0)
@@ -178,7 +193,8 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 				{
 					const float theta = fastAcos(rd.y), phi = fastAtan2(rd.z, rd.x);
 					const V3 sky = texLookupNI(p.scene.textures, p.scene.skybox, phi / (2.0f * PT_PI), theta / PT_PI);
-					L = L + thr * sky;
+					if constexpr (SHARE) color = color + thr * sky; // the warp's partial sums take every contribution as it comes
+					else L = L + thr * sky;
 				}
 				terminate = true;
 			}
@@ -189,7 +205,8 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 				const Surface s = surfaceAt<SMEM>(sv, h.prim, ro, rd, h.t);
 				const float4 *mp = reinterpret_cast<const float4 *>(p.scene.mats + h.prim);
 				const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2);
-				L = L + thr * mk(m1.x, m1.y, m1.z); // getEmitted, Material.inl:62-65
+				if constexpr (SHARE) color = color + thr * mk(m1.x, m1.y, m1.z); // getEmitted, Material.inl:62-65
+				else L = L + thr * mk(m1.x, m1.y, m1.z);
 				V3 base = mk(m0.x, m0.y, m0.z);
 				const uint32_t tex = __float_as_uint(m2.x), mtype = __float_as_uint(m2.y);
 				if (tex != 0 && tex <= p.scene.texCount)
@@ -220,7 +237,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 			}
 			if (terminate)
 			{
-				color = color + L;
+				if constexpr (!SHARE) color = color + L;
 				++sample;
 				alive = false;
 			}
@@ -361,6 +378,7 @@ int launchTrace(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t str
 	case 8: return PT_PICK(traceKernel, , 1, true);       // one pixel per WARP (lanes = samples), while-while
 	case 9: return PT_PICK(traceKernel, , 2, true);       // one pixel per warp, while-while + leaf parking
 	case 10: return PT_PICK(traceKernel, , 0, true);      // one pixel per warp, if/else traversal
+	case 11: return PT_PICK(traceKernel, , 3, true);      // EXPERIMENT
 	default: return PT_PICK(traceKernel, , 1, false);     // 4: one pixel per lane, while-while traversal
 	}
 #undef PT_PICK

@@ -50,7 +50,7 @@ __device__ __noinline__ PoolBest poolFoldPrim(const float4 *prims, uint32_t prim
 	V3 lo, ld;
 	toLocal(r0, r1, r2, o, d, lo, ld);
 	float t;
-	if (intersectLocal(__float_as_uint(meta.x), lo, ld, 0.001f, best.t, t))
+	if (intersectLocal<kHotExact>(__float_as_uint(meta.x), lo, ld, 0.001f, best.t, t))
 	{
 		bool take = true;
 		if (t == best.t && best.prim >= 0) take = !(__float_as_uint(meta.y) < __float_as_uint(sv.ld(prims + best.prim * 4 + 3).y));
@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(kPoolThreads, 1) traceKernelWP(const RenderPar
 #define PU(field, slot) poolU[(field) * K + (slot)]
 
 	const uint32_t totalPixels = p.width * p.height;
+	const float invW = 1.0f / float(p.width), invH = 1.0f / float(p.height);
 	const V3 camO = mk(p.cam.origin[0], p.cam.origin[1], p.cam.origin[2]);
 	constexpr float tMin = 0.001f;
 
@@ -340,9 +341,9 @@ __global__ void __launch_bounds__(kPoolThreads, 1) traceKernelWP(const RenderPar
 				const uint4 r = philoxNI(pixel, sampleIdx, 0u, p.seedLo, p.seedHi);
 				uint32_t px, py;
 				pixelToXY(pixel, p.width, p.height, px, py);
-				const float u = divExact(float(px) + uniform01(r.x), float(p.width)); // trace.cu:190
-				const float v = divExact(float(py) + uniform01(r.y), float(p.height));
-				const V3 d = cameraDir(p.cam, u, v);
+				const float u = (float(px) + uniform01(r.x)) * invW; // trace.cu:190
+				const float v = (float(py) + uniform01(r.y)) * invH;
+				const V3 d = cameraDir<kHotExact>(p.cam, u, v);
 				PF(F_OX, s) = camO.x; PF(F_OY, s) = camO.y; PF(F_OZ, s) = camO.z;
 				PF(F_DX, s) = d.x; PF(F_DY, s) = d.y; PF(F_DZ, s) = d.z;
 				PF(F_TX, s) = 1.0f; PF(F_TY, s) = 1.0f; PF(F_TZ, s) = 1.0f;

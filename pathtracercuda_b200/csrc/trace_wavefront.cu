@@ -79,7 +79,7 @@ __device__ WF_FOLD_INLINE WfBest wfFoldPrim(const float4 *prims, uint32_t prim, 
 	V3 lo, ld;
 	toLocal(r0, r1, r2, o, d, lo, ld);
 	float t;
-	if (intersectLocal(__float_as_uint(meta.x), lo, ld, 0.001f, best.t, t))
+	if (intersectLocal<kHotExact>(__float_as_uint(meta.x), lo, ld, 0.001f, best.t, t))
 	{
 		bool take = true;
 		if (t == best.t && best.prim >= 0) take = !(__float_as_uint(meta.y) < __float_as_uint(sv.ld(prims + best.prim * 4 + 3).y));
@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(kWfThreads, 1) traceKernelWF(const RenderParam
 	__syncthreads();
 
 	const uint32_t totalPixels = p.width * p.height;
+	const float invW = 1.0f / float(p.width), invH = 1.0f / float(p.height);
 	const V3 camO = mk(p.cam.origin[0], p.cam.origin[1], p.cam.origin[2]);
 	constexpr float tMin = 0.001f;
 	uint32_t rays = 0, nodeVisits = 0, primTests = 0, shades = 0, misses = 0;
@@ -579,9 +580,9 @@ __global__ void __launch_bounds__(kWfThreads, 1) traceKernelWF(const RenderParam
 					const uint4 r = philox4x32_10(pixel, sampleIdx, 0u, 0u, p.seedLo, p.seedHi);
 					uint32_t px, py;
 				pixelToXY(pixel, p.width, p.height, px, py);
-					const float u = divExact(float(px) + uniform01(r.x), float(p.width)); // trace.cu:190
-					const float v = divExact(float(py) + uniform01(r.y), float(p.height));
-					const V3 d = cameraDir(p.cam, u, v);
+					const float u = (float(px) + uniform01(r.x)) * invW; // trace.cu:190
+					const float v = (float(py) + uniform01(r.y)) * invH;
+					const V3 d = cameraDir<kHotExact>(p.cam, u, v);
 					SF(S_OX, s) = camO.x; SF(S_OY, s) = camO.y; SF(S_OZ, s) = camO.z;
 					SF(S_DX, s) = d.x; SF(S_DY, s) = d.y; SF(S_DZ, s) = d.z;
 					SF(S_TX, s) = 1.0f; SF(S_TY, s) = 1.0f; SF(S_TZ, s) = 1.0f;

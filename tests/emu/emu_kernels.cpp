@@ -171,15 +171,15 @@ uint64_t emu_render(void *p, const pt_camera_desc *cd, uint32_t width, uint32_t 
 			{
 				const uint32_t sampleIdx = sampleOffset + sample * sampleStride;
 				const uint4 r = philox4x32_10(pixel, sampleIdx, 0u, 0u, seedLo, seedHi);
-				const float u = divExact(float(x) + uniform01(r.x), float(width)), v = divExact(float(y) + uniform01(r.y), float(height));
+				const float u = (float(x) + uniform01(r.x)) * (1.0f / float(width)), v = (float(y) + uniform01(r.y)) * (1.0f / float(height));
 				uint32_t rz = r.z, rw = r.w;
-				V3 ro = camO, rd = cameraDir(cam, u, v), thr = mk(1.0f, 1.0f, 1.0f), L = mk(0.0f, 0.0f, 0.0f);
+				V3 ro = camO, rd = cameraDir<kHotExact>(cam, u, v), thr = mk(1.0f, 1.0f, 1.0f), L = mk(0.0f, 0.0f, 0.0f);
 				uint32_t bounce = 0;
 				while (true)
 				{
 					++raysTot;
 					uint32_t nv = 0, pt = 0;
-					const Hit h = closestHit<false, true>(sv, ro, rd, 0.001f, nv, pt);
+					const Hit h = closestHit<false, true, kHotExact>(sv, ro, rd, 0.001f, nv, pt);
 					nvTot += nv; ptTot += pt;
 					if (h.prim < 0)
 					{
