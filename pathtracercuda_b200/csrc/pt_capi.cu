@@ -266,7 +266,8 @@ int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ign
 		p.seedLo = uint32_t(c->seed);
 		p.seedHi = uint32_t(c->seed >> 32);
 		p.maxBounces = c->maxBounces;
-		p.regenLow = c->launch.regenLow > 0 ? uint32_t(c->launch.regenLow) : 8u;
+		p.regenLow = c->launch.regenLow > 0 ? uint32_t(c->launch.regenLow) : (c->launch.variant == 8 || c->launch.variant == 9 || c->launch.variant == 10 ? 8u : 16u);
+		p.beam = c->launch.beam < 0 ? (spp >= 256u ? 1u : 0u) : uint32_t(c->launch.beam != 0);
 		launches = launchTrace(p, c->launch, c->stream, &usedSmem);
 	}
 	CK(cudaEventRecord(c->evStop, c->stream));
@@ -362,6 +363,7 @@ int pt_set_option(pt_context *c, const char *key, double value)
 	else if (k == "trace_warps") c->launch.traceWarps = int(value);
 	else if (k == "ready_low") c->launch.readyLow = int(value);
 	else if (k == "regen_low") c->launch.regenLow = int(value);
+	else if (k == "beam") c->launch.beam = int(value);
 	else if (k == "pool_slots") c->launch.poolSlots = int(value);
 	else return setError(PT_E_INVALID, "pt_set_option: unknown option " + k);
 	return PT_OK;

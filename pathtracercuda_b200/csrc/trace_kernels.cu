@@ -25,7 +25,7 @@ namespace ptb
 // ---------------------------------------------------------------------------------------------------------------
 // the trace kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <bool SMEM, bool COUNT, int TRAV, bool SHARE>
+template <bool SMEM, bool COUNT, int TRAV, bool SHARE, bool SPLIT = false>
 __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderParams p)
 {
 	extern __shared__ __align__(128) float4 smemScene[];
@@ -44,6 +44,10 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 		sv.prims = p.scene.sceneBlob + size_t(p.scene.nodeCount) * 4;
 		sv.globalCount = p.scene.globalCount;
 	}
+
+	// SHARE: the leaves the camera rays of the warp's pixel can reach (beamLeaves), nearest first
+	__shared__ BeamEntry beamList[SHARE && TRAV == 1 ? kTraceThreads / 32 : 1][kBeamMax];
+	int nBeam = -1;
 
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t totalPixels = p.width * p.height;
@@ -108,6 +112,18 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 					if (next >= totalPixels) break;
 					pixel = uint32_t(next);
 					wNext = 0;
+					if constexpr (TRAV == 1)
+					{
+						if (p.beam)
+						{
+							uint32_t px, py;
+							pixelToXY(pixel, p.width, p.height, px, py);
+							const float m = 1.0f / 64.0f; // footprint widened: the jittered (s, t) are rounded products
+							nBeam = beamLeaves<SMEM>(sv.nodes, p.cam, (float(px) - m) * invW, (float(px) + 1.0f + m) * invW, (float(py) - m) * invH,
+							                         (float(py) + 1.0f + m) * invH, beamList[threadIdx.x >> 5], lane == 0);
+							__syncwarp();
+						}
+					}
 					continue;
 				}
 			}
@@ -144,7 +160,15 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 		generate = active && !alive;
 		}
 
-		if (SHARE ? (alive || generate) : active)
+		bool takePart = SHARE ? (alive || generate) : active;
+		if constexpr (SPLIT)
+		{
+			// SPLIT: a pass is EITHER for the camera rays just generated (coherent: same pixel, leaves from the pixel's beam list,
+			// no tree walk, usually the same material) OR for the scattered rays, where every live lane then walks the tree
+			// together.  Mixed passes kept ~11 of 32 lanes in the node loop: the lanes with camera rays had nothing to walk.
+			if (__any_sync(0xffffffffu, generate)) takePart = generate;
+		}
+		if (takePart)
 		{
 			// ---- generate (trace.cu:187-192) ----
 			if (generate)
@@ -166,22 +190,9 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 
 			// ---- traverse + intersect (trace.cu:112) ----
 			++rays;
-			Hit h;
-			if constexpr (TRAV == 3)
-			{
-				// EXPERIMENT: camera rays traced twice (how much of the step is camera-ray traversal?)
-				const int reps = bounce == 0 ? 2 : 1;
-#pragma unroll 1
-				for (int rep = 0; rep < reps; ++rep)
-				{
-					V3 o2 = ro;
-					o2.x += float(rep) * 1e-30f;
-					h = closestHitWW<SMEM, COUNT, false, kHotExact>(sv, o2, rd, 0.001f, nodeVisits, primTests);
-				}
-			}
-			else
-			h = TRAV == 0 ? closestHit<SMEM, COUNT, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests)
-			              : TRAV == 1 ? closestHitWW<SMEM, COUNT, false, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests)
+			const Hit h = TRAV == 0 ? closestHit<SMEM, COUNT, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests)
+			              : TRAV == 1 ? closestHitWW<SMEM, COUNT, false, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? threadIdx.x >> 5 : 0],
+			                                                                        SHARE && bounce == 0 ? nBeam : -1)
 			                          : closestHitWW<SMEM, COUNT, true, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests);
 
 			bool terminate;
@@ -361,16 +372,16 @@ int launchTrace(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t str
 	}
 	const size_t sceneBytes = (size_t(p.scene.nodeCount) + p.scene.primCount) * 64;
 	// leave room for 2+ CTAs per SM when the scene is small; a scene larger than the opt-in limit stays in L2/HBM
-	const bool smem = cfg.smemScene && sceneBytes + 1024 <= cfg.maxSmemOptin;
+	const bool smem = cfg.smemScene && sceneBytes + 8192 <= cfg.maxSmemOptin; // static shared memory: barrier + beam lists
 	if (usedSmem) *usedSmem = smem ? 1 : 0;
 	const size_t sb = smem ? sceneBytes : 0;
 #define PT_PICK(KERN, ...)                                                                                                        \
 	(smem ? (cfg.countWork ? launchKernel(KERN<true, true __VA_ARGS__>, p, cfg, sb, stream) : launchKernel(KERN<true, false __VA_ARGS__>, p, cfg, sb, stream)) \
 	      : (cfg.countWork ? launchKernel(KERN<false, true __VA_ARGS__>, p, cfg, sb, stream) : launchKernel(KERN<false, false __VA_ARGS__>, p, cfg, sb, stream)))
-	// default: one pixel per warp for renders long enough to amortise the drain at the end of every pixel (the last paths of
-	// a pixel run with the other lanes idle: ~half a path per spp/32 samples), one pixel per lane otherwise
+	// default: one pixel per warp (camera passes / scattered passes) for renders long enough to amortise the drain at the end of
+	// every pixel (the last paths of a pixel run with the other lanes idle: ~half a path per spp/32 samples), one pixel per lane otherwise
 	int variant = cfg.variant;
-	if (variant == 0) variant = p.spp >= 128 ? 8 : 4;
+	if (variant == 0) variant = p.spp >= 128 ? 12 : 4;
 	switch (variant)
 	{
 	case 1: return PT_PICK(traceKernel, , 0, false);      // per-lane if/else traversal
@@ -378,7 +389,7 @@ int launchTrace(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t str
 	case 8: return PT_PICK(traceKernel, , 1, true);       // one pixel per WARP (lanes = samples), while-while
 	case 9: return PT_PICK(traceKernel, , 2, true);       // one pixel per warp, while-while + leaf parking
 	case 10: return PT_PICK(traceKernel, , 0, true);      // one pixel per warp, if/else traversal
-	case 11: return PT_PICK(traceKernel, , 3, true);      // EXPERIMENT
+	case 12: return PT_PICK(traceKernel, , 1, true, true); // one pixel per warp, camera passes and scattered passes alternate
 	default: return PT_PICK(traceKernel, , 1, false);     // 4: one pixel per lane, while-while traversal
 	}
 #undef PT_PICK

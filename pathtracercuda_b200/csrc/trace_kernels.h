@@ -32,6 +32,7 @@ struct RenderParams
 	uint32_t seedLo, seedHi;
 	uint32_t maxBounces;
 	uint32_t regenLow = 1; // one-pixel-per-warp kernel: idle lanes wait until this many can start new samples together
+	uint32_t beam = 0;     // one-pixel-per-warp kernel: camera rays take their leaves from the pixel's beam list (trace_device.cuh)
 };
 
 struct LaunchConfig
@@ -39,8 +40,9 @@ struct LaunchConfig
 	int smCount = 148;
 	int smemScene = 1;   // stage the scene in shared memory when it fits
 	int countWork = 0;   // node/prim/shade/miss counters
-	int variant = 0;     // kernel variant (0 = default: 8 for spp >= 128, else 4.  4: one pixel per lane, while-while traversal; 1: if/else traversal;
+	int variant = 0;     // kernel variant (0 = default: 12 for spp >= 128, else 4.  4: one pixel per lane, while-while traversal; 1: if/else traversal;
 	                     //  5: + leaf parking; 8: one pixel per WARP (lanes = samples), while-while; 9/10: its other traversals;
+	                     //  12: 8 with separate passes for camera rays and scattered rays;
 	                     //  6: warp-pool wavefront, 7: CTA-pool warp-specialised wavefront - both measured slower)
 	int traceLow = 0;    // warp-pool: run shade/generate early when fewer than this many lanes could traverse (0 = 24)
 	int nodeLow = 0;     // warp-pool: the node loop leaves when fewer than this many lanes are still walking (0 = 24)
@@ -48,6 +50,7 @@ struct LaunchConfig
 	int traceWarps = 0;  // wavefront: warps per CTA that only traverse (0 = half of them); the others run the other stages
 	int readyLow = -1;   // wavefront: stage warps run partial batches while the READY queue holds fewer rays than this (-1 = 128)
 	int regenLow = 0;    // see RenderParams::regenLow (0 = default)
+	int beam = -1;       // pixel beams for the camera rays of the one-pixel-per-warp kernel: 1 on, 0 off, -1 = on from 256 spp
 	int poolSlots = 0;   // CTA-pool wavefront: path slots per CTA (0 = 1280 with the scene in shared memory, 1536 without)
 	size_t maxSmemOptin = 0;
 };

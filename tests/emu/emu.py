@@ -98,9 +98,16 @@ class Emu:
         self.L.emu_trace_rays(self.s, n, _p(o), _p(d), tmin, _p(idx), _p(t), _p(nrm))
         return idx, t, nrm
 
-    def render(self, cam, w, h, spp, seed=1984, sample_offset=0, sample_stride=1, accum=None, max_bounces=5):
+    def render(self, cam, w, h, spp, seed=1984, sample_offset=0, sample_stride=1, accum=None, max_bounces=5, beam=False):
+        """beam=True: camera rays take their leaves from the per-pixel beam lists (beamLeaves) instead of walking the tree;
+        self.beam_stats = (pixels, list entries, overflows, longest list) afterwards"""
         add = accum is not None
         if accum is None:
             accum = np.zeros((h, w, 4), np.float32)
+        self.L.emu_set_beam(int(beam))
         rays = self.L.emu_render(self.s, C.byref(cam), w, h, spp, seed, sample_offset, sample_stride, int(add), max_bounces, _p(accum))
+        st = (C.c_uint64 * 4)()
+        self.L.emu_beam_stats(st)
+        self.beam_stats = tuple(int(v) for v in st)
+        self.L.emu_set_beam(0)
         return accum, rays

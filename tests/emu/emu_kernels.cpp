@@ -60,6 +60,8 @@ struct EmuScene
 } // namespace
 
 static uint64_t g_lastWork[2] = { 0, 0 };
+static int g_beam = 0;              // emu_render: camera rays through the pixel beam lists (trace_device.cuh beamLeaves)
+static uint64_t g_beamStats[4] = { 0, 0, 0, 0 }; // pixels, list entries, overflows, longest list
 
 extern "C"
 {
@@ -167,6 +169,19 @@ uint64_t emu_render(void *p, const pt_camera_desc *cd, uint32_t width, uint32_t 
 		{
 			const uint32_t pixel = x + uint32_t(y) * width;
 			V3 color = mk(0.0f, 0.0f, 0.0f);
+			BeamEntry beam[kBeamMax];
+			int nBeam = -1;
+			if (g_beam)
+			{
+				const float m = 1.0f / 64.0f;
+				nBeam = beamLeaves<false>(sv.nodes, cam, (float(x) - m) * invW, (float(x) + 1.0f + m) * invW, (float(y) - m) * invH, (float(y) + 1.0f + m) * invH, beam, true);
+#pragma omp critical
+				{
+					++g_beamStats[0];
+					if (nBeam < 0) ++g_beamStats[2];
+					else { g_beamStats[1] += uint64_t(nBeam); g_beamStats[3] = std::max<uint64_t>(g_beamStats[3], uint64_t(nBeam)); }
+				}
+			}
 			for (uint32_t sample = 0; sample < spp; ++sample)
 			{
 				const uint32_t sampleIdx = sampleOffset + sample * sampleStride;
@@ -179,7 +194,8 @@ uint64_t emu_render(void *p, const pt_camera_desc *cd, uint32_t width, uint32_t 
 				{
 					++raysTot;
 					uint32_t nv = 0, pt = 0;
-					const Hit h = closestHit<false, true, kHotExact>(sv, ro, rd, 0.001f, nv, pt);
+					const Hit h = g_beam ? closestHitWW<false, true, false, kHotExact>(sv, ro, rd, 0.001f, nv, pt, beam, bounce == 0 ? nBeam : -1)
+					                     : closestHit<false, true, kHotExact>(sv, ro, rd, 0.001f, nv, pt);
 					nvTot += nv; ptTot += pt;
 					if (h.prim < 0)
 					{
@@ -230,4 +246,7 @@ void emu_fast_angles(size_t n, const float *y, const float *x, float *atan2Out, 
 }
 // node visits / primitive tests of the last emu_render (BVH quality experiments)
 void emu_last_work(uint64_t *out) { out[0] = g_lastWork[0]; out[1] = g_lastWork[1]; }
+// pixel beams on/off for emu_render + their statistics since the last call (pixels, entries, overflows, longest list)
+void emu_set_beam(int on) { g_beam = on; for (auto &v : g_beamStats) v = 0; }
+void emu_beam_stats(uint64_t *out) { for (int i = 0; i < 4; ++i) out[i] = g_beamStats[i]; }
 }

@@ -60,6 +60,22 @@ def test_render_matches_oracle_path_for_path(scene, W, H, spp):
     assert np.allclose(sum(p[..., :3] for p in parts), b[..., :3], rtol=1e-4, atol=1e-4)
 
 
+@pytest.mark.parametrize("scene,W,H", [("cornell_box", 48, 48), ("generated_scene", 160, 90)])
+def test_pixel_beam_lists_do_not_change_the_image(scene, W, H):
+    """camera rays that take their leaves from the per-pixel beam list (beamLeaves, trace_device.cuh) find the same closest
+    hits as the walk from the root: the image is bit-identical, the ray count equal, the lists short"""
+    objs, tex, sky_idx, cam = pt.parse_scene_py(f"{pt.ASSETS}/scenes/{scene}.json", W, H)
+    E = Emu(objs)
+    E.add_texture(imgio.read_png(pt.ASSETS + "/earth.png"))
+    if scene == "generated_scene":
+        E.set_skybox(E.add_texture(imgio.read_hdr(pt.ASSETS + "/skybox.hdr")))
+    a, ra = E.render(cam, W, H, 24)
+    b, rb = E.render(cam, W, H, 24, beam=True)
+    pixels, entries, overflows, longest = E.beam_stats
+    assert ra == rb and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert pixels == W * H and overflows == 0 and longest <= 16 and entries > 0
+
+
 def test_quirks_match_oracle():
     """cube entered from inside reports t = tMin (Q2); sphere accepts its far root beyond tMax (Hittable.inl:152-157)"""
     objs = [pt.make_object("CUBE"), pt.make_object("SPHERE", position=(5, 0, 0)), pt.make_object("QUAD", position=(5, 0.5, 0), rotation_deg=(0, 0, 90))]

@@ -173,10 +173,17 @@ def test_kernel_variants_bit_identical():
     warp = [(v, run(v, 80)) for v in (8, 9, 10, 8)]
     for v, img in warp:
         assert np.array_equal(bits(warp[0][1]), bits(img)), v
+    # camera passes / scattered passes hand the samples to the lanes in another order: its own sums, same from run to run
+    split = run(12, 80)
+    assert np.array_equal(bits(split), bits(run(12, 80))) and np.allclose(split, lane, rtol=2e-5, atol=1e-7)
     assert np.allclose(warp[0][1], lane, rtol=2e-5, atol=1e-7)
     assert np.allclose(run(8, 80, regen_low=1), lane, rtol=2e-5, atol=1e-7)
     assert np.allclose(run(8, 80, regen_low=32), lane, rtol=2e-5, atol=1e-7)
-    assert np.array_equal(bits(run(0, 128)), bits(run(8, 128)))
+    assert np.array_equal(bits(run(0, 128)), bits(run(12, 128)))
+    # pixel beams (camera rays take their leaves from the pixel's list instead of walking the tree): same closest hits
+    assert np.array_equal(bits(run(8, 80, beam=1)), bits(run(8, 80, beam=0)))
+    assert np.array_equal(bits(run(12, 80, beam=1)), bits(run(12, 80, beam=0)))
+    assert np.array_equal(bits(run(0, 256)), bits(run(12, 256, beam=0)))
     assert np.allclose(run(8, 5), run(4, 5), rtol=2e-5, atol=1e-7)  # fewer samples than lanes
     with pt.Pathtracer(320, 180) as P:  # shared-memory scene vs global-memory scene
         cam = P.loadSceneFile(f"{pt.ASSETS}/scenes/generated_scene.json", cwd=pt.ASSETS)
