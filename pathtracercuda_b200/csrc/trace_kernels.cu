@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 				if (p.scene.skybox != 0)
 				{
 					const float theta = fastAcos(rd.y), phi = fastAtan2(rd.z, rd.x);
-					const V3 sky = texLookupNI(p.scene.textures, p.scene.skybox, phi / (2.0f * PT_PI), theta / PT_PI);
+					const V3 sky = texLookupNI(p.scene.textures, p.scene.skybox, phi * (0.5f / PT_PI), theta * (1.0f / PT_PI));
 					if constexpr (SHARE) color = color + thr * sky; // the warp's partial sums take every contribution as it comes
 					else L = L + thr * sky;
 				}

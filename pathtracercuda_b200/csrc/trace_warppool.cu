@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kPoolThreads, 1) traceKernelWP(const RenderPar
 						{
 							const V3 mrd = mk(PF(F_DX, s), PF(F_DY, s), PF(F_DZ, s)), thr = mk(PF(F_TX, s), PF(F_TY, s), PF(F_TZ, s));
 							const float theta = fastAcos(mrd.y), phi = fastAtan2(mrd.z, mrd.x);
-							const V3 sky = texLookupNI(p.scene.textures, p.scene.skybox, phi / (2.0f * PT_PI), theta / PT_PI);
+							const V3 sky = texLookupNI(p.scene.textures, p.scene.skybox, phi * (0.5f / PT_PI), theta * (1.0f / PT_PI));
 							L = L + thr * sky;
 						}
 					}

@@ -538,7 +538,7 @@ __global__ void __launch_bounds__(kWfThreads, 1) traceKernelWF(const RenderParam
 							{
 								const V3 mrd = mk(SF(S_DX, s), SF(S_DY, s), SF(S_DZ, s)), thr = mk(SF(S_TX, s), SF(S_TY, s), SF(S_TZ, s));
 								const float theta = fastAcos(mrd.y), phi = fastAtan2(mrd.z, mrd.x);
-								const V3 sky = texLookup(p.scene.textures, p.scene.skybox, phi / (2.0f * PT_PI), theta / PT_PI);
+								const V3 sky = texLookup(p.scene.textures, p.scene.skybox, phi * (0.5f / PT_PI), theta * (1.0f / PT_PI));
 								L = L + thr * sky;
 							}
 						}

@@ -202,7 +202,7 @@ uint64_t emu_render(void *p, const pt_camera_desc *cd, uint32_t width, uint32_t 
 						if (s->skybox != 0)
 						{
 							const float theta = fastAcos(rd.y), phi = fastAtan2(rd.z, rd.x);
-							const V3 sky = texLookup(s->tex, s->skybox, phi / (2.0f * PT_PI), theta / PT_PI);
+							const V3 sky = texLookup(s->tex, s->skybox, phi * (0.5f / PT_PI), theta * (1.0f / PT_PI));
 							L = L + thr * sky;
 						}
 						break;
