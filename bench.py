@@ -310,7 +310,7 @@ def main():
         peak_tops = sms * 128 * f_mhz * 1e6 / 1e12          # FP32 lane-instruction slots per second (an FMA counts once)
         kernel_ms = float(np.mean(ms_steps))                # this rank's trace kernel (+ reduce) per launch
         achieved = rays_steps[0] * ops_per_ray / (kernel_ms * 1e-3) / 1e12
-        prof = os.path.join(ROOT, "profiles", "r01_trace_kernel_summary.json")
+        prof = os.path.join(ROOT, "profiles", "r01b_trace_kernel_summary.json")
         traffic = None
         try:
             traffic = json.load(open(prof)).get("dram_bytes_per_launch")

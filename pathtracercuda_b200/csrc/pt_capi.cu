@@ -41,7 +41,7 @@ struct pt_context
 	// scene
 	float4 *sceneBlob = nullptr;
 	Mat *mats = nullptr;
-	uint32_t nodeCount = 0, primCount = 0, bvhDepth = 0, globalCount = 0, maxGlobal = ptb::kMaxGlobalPrims;
+	uint32_t nodeCount = 0, treeNodeCount = 0, primCount = 0, bvhDepth = 0, globalCount = 0, maxGlobal = ptb::kMaxGlobalPrims;
 	// textures
 	std::vector<void *> texMem;
 	TexDesc texHost[kMaxTextures];
@@ -168,8 +168,9 @@ int pt_set_scene(pt_context *c, size_t count, const pt_object_desc *objects)
 	c->nodeCount = uint32_t(cs.nodes.size());
 	c->primCount = uint32_t(cs.prims.size());
 	c->globalCount = cs.globalCount;
+	c->treeNodeCount = cs.treeNodeCount;
 	c->bvhDepth = cs.depth;
-	c->stats.bvh_nodes = c->nodeCount;
+	c->stats.bvh_nodes = c->treeNodeCount;
 	c->stats.bvh_depth = c->bvhDepth;
 	c->stats.scene_bytes = uint32_t(nodeBytes + primBytes + cs.mats.size() * sizeof(Mat));
 	return PT_OK;
@@ -230,6 +231,7 @@ static SceneDev sceneDev(const pt_context *c)
 	s.nodeCount = c->nodeCount;
 	s.primCount = c->primCount;
 	s.globalCount = c->globalCount;
+	s.treeNodeCount = c->treeNodeCount;
 	s.texCount = c->textureCount;
 	s.skybox = (c->skybox <= c->textureCount) ? c->skybox : 0;
 	return s;

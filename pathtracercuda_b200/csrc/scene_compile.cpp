@@ -408,6 +408,29 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 		}
 		out.nodes.swap(renum);
 	}
+	// the hoisted primitives' boxes, two per record, behind the tree: the pixel-beam walk decides with them which hoisted
+	// primitives the camera rays of a pixel have to test at all
+	out.treeNodeCount = uint32_t(out.nodes.size());
+	for (size_t g = 0; g < nGlobal; g += 2)
+	{
+		Node nd;
+		for (int c = 0; c < 2; ++c)
+		{
+			float *f = nd.f + 6 * c;
+			if (g + c < nGlobal)
+			{
+				for (int k = 0; k < 3; ++k) { f[k] = bp[g + c].box.mn[k]; f[3 + k] = bp[g + c].box.mx[k]; }
+				nd.child[c] = b.leafRef(g + c, 1);
+			}
+			else
+			{
+				for (int k = 0; k < 3; ++k) { f[k] = FLT_MAX; f[3 + k] = FLT_MAX; }
+				nd.child[c] = kEmptyChild;
+			}
+		}
+		nd.pad[0] = nd.pad[1] = 0;
+		out.nodes.push_back(nd);
+	}
 	// min/max -> centre / half extent, padded outwards: the traversal computes t_c = c*inv - o*inv in fp32, so the box
 	// must absorb a few ulp of |c|, of its own size and of the scene scale (ray origins) to stay conservative
 	{

@@ -10,7 +10,9 @@ namespace ptb
 
 struct CompiledScene
 {
-	std::vector<Node> nodes;
+	std::vector<Node> nodes;  // nodes[0..treeNodeCount): the tree; then one record per PAIR of hoisted primitives (their boxes + leaf
+	                          // references), which no tree node points to: only the pixel-beam walk reads them (trace_device.cuh)
+	uint32_t treeNodeCount = 0;
 	std::vector<Prim> prims; // BVH order
 	std::vector<Mat> mats;   // BVH order (parallel to prims)
 	uint32_t depth = 0;      // interior-node depth (max traversal stack = depth)

@@ -37,16 +37,20 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 		sv.nodes = smemScene;
 		sv.prims = smemScene + size_t(p.scene.nodeCount) * 4;
 		sv.globalCount = p.scene.globalCount;
+		sv.extraRootBegin = p.scene.treeNodeCount;
+		sv.extraRootEnd = p.scene.nodeCount;
 	}
 	else
 	{
 		sv.nodes = p.scene.sceneBlob;
 		sv.prims = p.scene.sceneBlob + size_t(p.scene.nodeCount) * 4;
 		sv.globalCount = p.scene.globalCount;
+		sv.extraRootBegin = p.scene.treeNodeCount;
+		sv.extraRootEnd = p.scene.nodeCount;
 	}
 
 	// SHARE: the leaves the camera rays of the warp's pixel can reach (beamLeaves), nearest first
-	__shared__ BeamEntry beamList[SHARE && TRAV == 1 ? kTraceThreads / 32 : 1][kBeamMax];
+	__shared__ BeamEntry beamList[SHARE && TRAV >= 1 ? kTraceThreads / 32 : 1][kBeamMax];
 	int nBeam = -1;
 
 	const uint32_t lane = threadIdx.x & 31u;
@@ -61,6 +65,8 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 	uint32_t bounce = 0, rz = 0, rw = 0, sampleIdx = 0;
 	uint32_t rays = 0, nodeVisits = 0, primTests = 0, shades = 0, misses = 0;
 	uint32_t wNext = p.spp; // SHARE: next sample of the warp's pixel to hand out (warp-uniform)
+	unsigned long long passStat[6] = { 0, 0, 0, 0, 0, 0 }; // COUNT + SPLIT (lane 0): camera passes, lanes, clocks; scattered passes, lanes, clocks
+	const long long kernelT0 = COUNT && SPLIT ? clock64() : 0;
 
 	while (true)
 	{
@@ -112,14 +118,14 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 					if (next >= totalPixels) break;
 					pixel = uint32_t(next);
 					wNext = 0;
-					if constexpr (TRAV == 1)
+					if constexpr (TRAV >= 1)
 					{
 						if (p.beam)
 						{
 							uint32_t px, py;
 							pixelToXY(pixel, p.width, p.height, px, py);
 							const float m = 1.0f / 64.0f; // footprint widened: the jittered (s, t) are rounded products
-							nBeam = beamLeaves<SMEM>(sv.nodes, p.cam, (float(px) - m) * invW, (float(px) + 1.0f + m) * invW, (float(py) - m) * invH,
+							nBeam = beamLeaves<SMEM>(sv.nodes, p.scene.treeNodeCount, p.scene.nodeCount, p.cam, (float(px) - m) * invW, (float(px) + 1.0f + m) * invW, (float(py) - m) * invH,
 							                         (float(py) + 1.0f + m) * invH, beamList[threadIdx.x >> 5], lane == 0);
 							__syncwarp();
 						}
@@ -168,6 +174,16 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 			// together.  Mixed passes kept ~11 of 32 lanes in the node loop: the lanes with camera rays had nothing to walk.
 			if (__any_sync(0xffffffffu, generate)) takePart = generate;
 		}
+		// COUNT + SPLIT: passes, participating lanes and clocks per pass kind (tools/exp.py prints them)
+		long long passT0 = 0;
+		bool camPassNow = false;
+		if constexpr (COUNT && SPLIT)
+		{
+			camPassNow = __any_sync(0xffffffffu, generate);
+			const uint32_t part = __popc(__ballot_sync(0xffffffffu, takePart));
+			if (lane == 0) { passStat[camPassNow ? 0 : 3] += 1; passStat[camPassNow ? 1 : 4] += part; }
+			passT0 = clock64();
+		}
 		if (takePart)
 		{
 			// ---- generate (trace.cu:187-192) ----
@@ -193,7 +209,8 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 			const Hit h = TRAV == 0 ? closestHit<SMEM, COUNT, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests)
 			              : TRAV == 1 ? closestHitWW<SMEM, COUNT, false, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? threadIdx.x >> 5 : 0],
 			                                                                        SHARE && bounce == 0 ? nBeam : -1)
-			                          : closestHitWW<SMEM, COUNT, true, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests);
+			                          : closestHitWW<SMEM, COUNT, true, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? threadIdx.x >> 5 : 0],
+			                                                                       SHARE && bounce == 0 ? nBeam : -1);
 
 			bool terminate;
 			if (h.prim < 0)
@@ -253,6 +270,11 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 				alive = false;
 			}
 		}
+		if constexpr (COUNT && SPLIT)
+		{
+			__syncwarp();
+			if (lane == 0) passStat[camPassNow ? 2 : 5] += (unsigned long long)(clock64() - passT0);
+		}
 	}
 
 	// ---- counters: one atomic per warp ----
@@ -260,6 +282,14 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) r64 += __shfl_xor_sync(0xffffffffu, r64, o);
 	if (lane == 0) atomicAdd(&p.counters[kCtrRays], r64);
+	if constexpr (COUNT && SPLIT)
+	{
+		if (lane == 0)
+		{
+			for (int k = 0; k < 6; ++k) atomicAdd(&p.counters[kCtrTraceRounds + k], passStat[k]);
+			atomicAdd(&p.counters[kCtrTraceRounds + 6], (unsigned long long)(clock64() - kernelT0));
+		}
+	}
 	if (COUNT)
 	{
 		unsigned long long c[4] = { nodeVisits, primTests, shades, misses };
@@ -282,6 +312,8 @@ __global__ void __launch_bounds__(kThreads) primaryKernel(SceneDev scene, Camera
 	sv.nodes = scene.sceneBlob;
 	sv.prims = scene.sceneBlob + size_t(scene.nodeCount) * 4;
 	sv.globalCount = scene.globalCount;
+	sv.extraRootBegin = scene.treeNodeCount;
+	sv.extraRootEnd = scene.nodeCount;
 	const uint32_t total = width * height;
 	uint32_t nv = 0, pt = 0;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
@@ -303,6 +335,8 @@ __global__ void __launch_bounds__(kThreads) traceRaysKernel(SceneDev scene, uint
 	sv.nodes = scene.sceneBlob;
 	sv.prims = scene.sceneBlob + size_t(scene.nodeCount) * 4;
 	sv.globalCount = scene.globalCount;
+	sv.extraRootBegin = scene.treeNodeCount;
+	sv.extraRootEnd = scene.nodeCount;
 	uint32_t nv = 0, pt = 0;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
 	{
@@ -390,6 +424,7 @@ int launchTrace(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t str
 	case 9: return PT_PICK(traceKernel, , 2, true);       // one pixel per warp, while-while + leaf parking
 	case 10: return PT_PICK(traceKernel, , 0, true);      // one pixel per warp, if/else traversal
 	case 12: return PT_PICK(traceKernel, , 1, true, true); // one pixel per warp, camera passes and scattered passes alternate
+	case 13: return PT_PICK(traceKernel, , 2, true, true); // 12 + leaf parking
 	default: return PT_PICK(traceKernel, , 1, false);     // 4: one pixel per lane, while-while traversal
 	}
 #undef PT_PICK

@@ -19,6 +19,7 @@ struct SceneDev
 	const TexDesc *textures = nullptr;
 	uint32_t nodeCount = 0, primCount = 0, texCount = 0, skybox = 0;
 	uint32_t globalCount = 0; // prims[0..globalCount): tested by every ray before the traversal (pt_types.h)
+	uint32_t treeNodeCount = 0; // nodes[treeNodeCount..nodeCount): boxes of the hoisted primitives, for the pixel-beam walk only
 };
 
 struct RenderParams

@@ -54,6 +54,8 @@ struct EmuScene
 		sv.nodes = blob.data();
 		sv.prims = blob.data() + cs.nodes.size() * 4;
 		sv.globalCount = cs.globalCount;
+		sv.extraRootBegin = cs.treeNodeCount;
+		sv.extraRootEnd = uint32_t(cs.nodes.size());
 		return sv;
 	}
 };
@@ -93,13 +95,13 @@ uint32_t emu_global_count(void *p) { return ((EmuScene *)p)->cs.globalCount; }
 void emu_scene_info(void *p, uint32_t *nodes, uint32_t *depth, uint32_t *leaves)
 {
 	EmuScene *s = (EmuScene *)p;
-	*nodes = (uint32_t)s->cs.nodes.size(); *depth = s->cs.depth; *leaves = s->cs.leafCount;
+	*nodes = (uint32_t)s->cs.treeNodeCount; *depth = s->cs.depth; *leaves = s->cs.leafCount;
 }
 // raw compiled arrays for structural validation by the tests (Node = 16 x 4 bytes, Prim = 16 x 4 bytes)
 void emu_scene_arrays(void *p, void *nodesOut, void *primsOut)
 {
 	EmuScene *s = (EmuScene *)p;
-	memcpy(nodesOut, s->cs.nodes.data(), s->cs.nodes.size() * 64);
+	memcpy(nodesOut, s->cs.nodes.data(), size_t(s->cs.treeNodeCount) * 64); // the tree (not the hoisted-box records behind it)
 	memcpy(primsOut, s->cs.prims.data(), s->cs.prims.size() * 64);
 }
 
@@ -174,7 +176,7 @@ uint64_t emu_render(void *p, const pt_camera_desc *cd, uint32_t width, uint32_t 
 			if (g_beam)
 			{
 				const float m = 1.0f / 64.0f;
-				nBeam = beamLeaves<false>(sv.nodes, cam, (float(x) - m) * invW, (float(x) + 1.0f + m) * invW, (float(y) - m) * invH, (float(y) + 1.0f + m) * invH, beam, true);
+				nBeam = beamLeaves<false>(sv.nodes, s->cs.treeNodeCount, uint32_t(s->cs.nodes.size()), cam, (float(x) - m) * invW, (float(x) + 1.0f + m) * invW, (float(y) - m) * invH, (float(y) + 1.0f + m) * invH, beam, true);
 #pragma omp critical
 				{
 					++g_beamStats[0];
