@@ -37,16 +37,12 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 		sv.nodes = smemScene;
 		sv.prims = smemScene + size_t(p.scene.nodeCount) * 4;
 		sv.globalCount = p.scene.globalCount;
-		sv.extraRootBegin = p.scene.treeNodeCount;
-		sv.extraRootEnd = p.scene.nodeCount;
 	}
 	else
 	{
 		sv.nodes = p.scene.sceneBlob;
 		sv.prims = p.scene.sceneBlob + size_t(p.scene.nodeCount) * 4;
 		sv.globalCount = p.scene.globalCount;
-		sv.extraRootBegin = p.scene.treeNodeCount;
-		sv.extraRootEnd = p.scene.nodeCount;
 	}
 
 	// SHARE: the leaves the camera rays of the warp's pixel can reach (beamLeaves), nearest first
@@ -312,8 +308,6 @@ __global__ void __launch_bounds__(kThreads) primaryKernel(SceneDev scene, Camera
 	sv.nodes = scene.sceneBlob;
 	sv.prims = scene.sceneBlob + size_t(scene.nodeCount) * 4;
 	sv.globalCount = scene.globalCount;
-	sv.extraRootBegin = scene.treeNodeCount;
-	sv.extraRootEnd = scene.nodeCount;
 	const uint32_t total = width * height;
 	uint32_t nv = 0, pt = 0;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
@@ -335,8 +329,6 @@ __global__ void __launch_bounds__(kThreads) traceRaysKernel(SceneDev scene, uint
 	sv.nodes = scene.sceneBlob;
 	sv.prims = scene.sceneBlob + size_t(scene.nodeCount) * 4;
 	sv.globalCount = scene.globalCount;
-	sv.extraRootBegin = scene.treeNodeCount;
-	sv.extraRootEnd = scene.nodeCount;
 	uint32_t nv = 0, pt = 0;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
 	{

@@ -54,8 +54,6 @@ struct EmuScene
 		sv.nodes = blob.data();
 		sv.prims = blob.data() + cs.nodes.size() * 4;
 		sv.globalCount = cs.globalCount;
-		sv.extraRootBegin = cs.treeNodeCount;
-		sv.extraRootEnd = uint32_t(cs.nodes.size());
 		return sv;
 	}
 };
