@@ -45,6 +45,9 @@ struct pt_context
 	// textures
 	std::vector<void *> texMem;
 	TexDesc texHost[kMaxTextures];
+	std::vector<cudaArray_t> texArrays;
+	std::vector<cudaTextureObject_t> texObjects;
+	int texUnit = 1; // filter textures with the texture unit (0: in software from linear memory)
 	TexDesc *texDev = nullptr;
 	uint32_t textureCount = 0, skybox = 0;
 	// state mirrored from the reference
@@ -136,6 +139,8 @@ void pt_destroy(pt_context *c)
 	if (c->sceneBlob) cudaFree(c->sceneBlob);
 	if (c->mats) cudaFree(c->mats);
 	for (void *p : c->texMem) cudaFree(p);
+	for (cudaTextureObject_t o : c->texObjects) cudaDestroyTextureObject(o);
+	for (cudaArray_t a : c->texArrays) cudaFreeArray(a);
 	if (c->evStart) cudaEventDestroy(c->evStart);
 	if (c->evStop) cudaEventDestroy(c->evStop);
 	if (c->stream) cudaStreamDestroy(c->stream);
@@ -176,6 +181,18 @@ int pt_set_scene(pt_context *c, size_t count, const pt_object_desc *objects)
 	return PT_OK;
 }
 
+// device copy of the texture table; with tex_unit = 0 the texture objects are left out and the kernels filter in software
+static int uploadTextureTable(pt_context *c)
+{
+	TexDesc tmp[kMaxTextures];
+	memcpy(tmp, c->texHost, sizeof tmp);
+	if (!c->texUnit)
+		for (TexDesc &t : tmp) t.texObj = 0;
+	if (cudaMemcpyAsync(c->texDev, tmp, sizeof tmp, cudaMemcpyHostToDevice, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)
+		return setError(PT_E_CUDA, "pt_load_texture: table upload failed");
+	return PT_OK;
+}
+
 uint32_t pt_load_texture_mem(pt_context *c, uint32_t width, uint32_t height, int is_hdr, const void *rgba)
 {
 	if (!c || !rgba || width == 0 || height == 0) return 0;
@@ -196,13 +213,46 @@ uint32_t pt_load_texture_mem(pt_context *c, uint32_t width, uint32_t height, int
 	t.height = height;
 	t.isHdr = is_hdr ? 1u : 0u;
 	t.pad = 0;
+	t.texObj = 0;
 	c->texMem.push_back(dev);
-	if (cudaMemcpyAsync(c->texDev, c->texHost, sizeof c->texHost, cudaMemcpyHostToDevice, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess)
+	// the same texels behind a texture object (Pathtracer.cpp:259-288: array, wrap U / clamp V, linear filter, normalised
+	// coordinates; 8-bit texels read as normalised floats)
 	{
-		setError(PT_E_CUDA, "pt_load_texture: table upload failed");
-		return 0;
+		cudaChannelFormatDesc fmt = is_hdr ? cudaCreateChannelDesc<float4>() : cudaCreateChannelDesc<uchar4>();
+		cudaArray_t arr = nullptr;
+		cudaTextureObject_t obj = 0;
+		bool ok = cudaMallocArray(&arr, &fmt, width, height) == cudaSuccess;
+		const size_t pitch = size_t(width) * (is_hdr ? 16 : 4);
+		ok = ok && cudaMemcpy2DToArray(arr, 0, 0, rgba, pitch, pitch, height, cudaMemcpyHostToDevice) == cudaSuccess;
+		if (ok)
+		{
+			cudaResourceDesc rd;
+			memset(&rd, 0, sizeof rd);
+			rd.resType = cudaResourceTypeArray;
+			rd.res.array.array = arr;
+			cudaTextureDesc td;
+			memset(&td, 0, sizeof td);
+			td.addressMode[0] = cudaAddressModeWrap;
+			td.addressMode[1] = cudaAddressModeClamp;
+			td.filterMode = cudaFilterModeLinear;
+			td.readMode = is_hdr ? cudaReadModeElementType : cudaReadModeNormalizedFloat;
+			td.normalizedCoords = 1;
+			ok = cudaCreateTextureObject(&obj, &rd, &td, nullptr) == cudaSuccess;
+		}
+		if (!ok)
+		{
+			if (arr) cudaFreeArray(arr);
+			cudaGetLastError();
+			setError(PT_E_CUDA, "pt_load_texture: texture object creation failed");
+			return 0;
+		}
+		t.texObj = (unsigned long long)obj;
+		c->texArrays.push_back(arr);
+		c->texObjects.push_back(obj);
 	}
-	return ++c->textureCount;
+	++c->textureCount;
+	if (uploadTextureTable(c) != PT_OK) { --c->textureCount; return 0; }
+	return c->textureCount;
 }
 
 uint32_t pt_load_texture(pt_context *c, const char *path)
@@ -366,6 +416,7 @@ int pt_set_option(pt_context *c, const char *key, double value)
 	else if (k == "ready_low") c->launch.readyLow = int(value);
 	else if (k == "regen_low") c->launch.regenLow = int(value);
 	else if (k == "beam") c->launch.beam = int(value);
+	else if (k == "tex_unit") { c->texUnit = value != 0; return uploadTextureTable(c); }
 	else if (k == "pool_slots") c->launch.poolSlots = int(value);
 	else return setError(PT_E_INVALID, "pt_set_option: unknown option " + k);
 	return PT_OK;

@@ -76,7 +76,12 @@ struct TexDesc
 	uint32_t height;
 	uint32_t isHdr;
 	uint32_t pad;
+	// the same texels as a CUDA texture object (array + linear filter, wrap U / clamp V, normalised coordinates: the reference's
+	// own setup, Pathtracer.cpp:259-288): ONE TEX instruction per tap instead of ~120 for four loads + fp32 filtering.
+	// 0 = filter in software from `texels` (option tex_unit=0, and the CPU emulation).
+	unsigned long long texObj;
 };
+static_assert(sizeof(TexDesc) == 32, "TexDesc must be 32 bytes");
 
 struct CameraDev
 {

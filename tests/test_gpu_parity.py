@@ -278,6 +278,23 @@ def test_textures_and_skybox():
     assert (rel.max(-1) > 2e-3).mean() < 0.03 and abs(a[..., :3].mean() / b[..., :3].mean() - 1) < 2e-3
 
 
+def test_texture_unit_matches_software_filter():
+    """texture taps through the texture unit (one TEX instruction, 1.8 fixed-point filter weights - the reference's own
+    path) against the fp32 software filter over the packed texels (option tex_unit=0): same image up to the weights'
+    1/256-texel quantisation"""
+    imgs = []
+    for unit in (1, 0):
+        with pt.Pathtracer(240, 135) as P:
+            cam = P.loadSceneFile(f"{pt.ASSETS}/scenes/generated_scene.json", cwd=pt.ASSETS)
+            P.setOption("tex_unit", unit)
+            P.render(cam, 64, True)
+            imgs.append(P.getHDRMean()[..., :3])
+    hw, sw = imgs
+    assert not np.array_equal(hw, sw)  # the option does switch paths
+    rel = np.abs(hw - sw) / (np.abs(sw) + 0.05)
+    assert (rel.max(-1) > 5e-3).mean() < 0.02 and abs(hw.mean() / sw.mean() - 1) < 1e-3
+
+
 def test_cli_end_to_end(tmp_path):
     """the drop-in surface: same flags, same stdout lines, PNG / HDR files that decode to the API's images"""
     W, H, spp = 160, 90, 24
