@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 	uint32_t rays = 0, nodeVisits = 0, primTests = 0, shades = 0, misses = 0;
 	uint32_t wNext = p.spp; // SHARE: next sample of the warp's pixel to hand out (warp-uniform)
 	unsigned long long passStat[6] = { 0, 0, 0, 0, 0, 0 }; // COUNT + SPLIT (lane 0): camera passes, lanes, clocks; scattered passes, lanes, clocks
+	unsigned long long travClk[2] = { 0, 0 };               // COUNT + SPLIT: clocks up to the end of the traversal, camera / scattered passes
 	const long long kernelT0 = COUNT && SPLIT ? clock64() : 0;
 
 	while (true)
@@ -208,6 +209,11 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 			                          : closestHitWW<SMEM, COUNT, true, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? threadIdx.x >> 5 : 0],
 			                                                                       SHARE && bounce == 0 ? nBeam : -1);
 
+			if constexpr (COUNT && SPLIT)
+			{
+				// clocks of the traversal part of the pass, as seen by the first participating lane (debug statistics)
+				if (lane == uint32_t(__ffs(__activemask()) - 1)) travClk[camPassNow ? 0 : 1] += (unsigned long long)(clock64() - passT0);
+			}
 			bool terminate;
 			if (h.prim < 0)
 			{
@@ -285,6 +291,8 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 			for (int k = 0; k < 6; ++k) atomicAdd(&p.counters[kCtrTraceRounds + k], passStat[k]);
 			atomicAdd(&p.counters[kCtrTraceRounds + 6], (unsigned long long)(clock64() - kernelT0));
 		}
+		atomicAdd(&p.counters[kCtrTraceRounds + 7], travClk[0]);
+		atomicAdd(&p.counters[kCtrTraceRounds + 8], travClk[1]);
 	}
 	if (COUNT)
 	{

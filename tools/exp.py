@@ -29,7 +29,8 @@ with pt.Pathtracer(W, H) as P:
         cp, cl, cc, sp_, sl, sc, tot = [raw[8 + k] for k in range(7)]
         print(json.dumps({"camera_passes_per_ksample": round(1e3 * cp / st.samples, 2), "lanes_per_camera_pass": round(cl / max(cp, 1), 2), "clocks_per_camera_pass": round(cc / max(cp, 1), 1),
                           "scattered_passes_per_ksample": round(1e3 * sp_ / st.samples, 2), "lanes_per_scattered_pass": round(sl / max(sp_, 1), 2), "clocks_per_scattered_pass": round(sc / max(sp_, 1), 1),
-                          "share_camera": round(cc / tot, 3), "share_scattered": round(sc / tot, 3), "share_other": round(1 - (cc + sc) / tot, 3)}))
+                          "share_camera": round(cc / tot, 3), "share_scattered": round(sc / tot, 3), "share_other": round(1 - (cc + sc) / tot, 3),
+                          "traversal_share_of_camera_pass": round(raw[15] / max(cc, 1), 3), "traversal_share_of_scattered_pass": round(raw[16] / max(sc, 1), 3)}))
     elif hasattr(P.L, "pt_debug_counters") and P.L.pt_debug_counters(P.h, raw, 24) == 24 and raw[8]:
         r = list(raw)
         names = ["traceRounds", "traceWalkers", "nodeIters", "shadeExec", "shadeSlots", "genExec", "genSlots", "leafExec", "leafSlots", "idle", "blocked", "refills", "refillSlots"]
