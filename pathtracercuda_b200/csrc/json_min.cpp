@@ -1,6 +1,9 @@
 #include "json_min.h"
 #include <cstdlib>
 #include <cstring>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 namespace ptb
 {
@@ -153,7 +156,70 @@ struct Parser
 		}
 		return true;
 	}
-	bool value(JsonValue &v)
+	bool value(JsonValue &v);
+
+	// A LARGE array (the "objects" list of a million-object scene is hundreds of megabytes) is split at its top-level
+	// commas by one cheap structural scan and its elements are parsed by all cores, each with its own Parser over the
+	// same text.  Returns false (nothing consumed) when the array is small, when already inside a parallel region, or
+	// when anything looks wrong - the sequential path then parses it and reports errors with the usual byte offsets.
+	bool parallelArray(JsonValue &v)
+	{
+#ifdef _OPENMP
+		if (n - i < (size_t(1) << 22) || omp_in_parallel() || omp_get_max_threads() < 2) return false;
+		std::vector<size_t> starts;
+		size_t j = i + 1, end = 0;
+		int d = 0;
+		starts.push_back(j);
+		static const struct Structural { bool is[256]; Structural() : is() { for (const char *q = "\"[]{},"; *q; ++q) is[(unsigned char)*q] = true; } } structural;
+		for (; j < n; ++j)
+		{
+			while (j < n && !structural.is[(unsigned char)s[j]]) ++j; // digits, letters, blanks: nothing to track
+			if (j >= n) break;
+			const char ch = s[j];
+			if (ch == '"')
+			{
+				for (++j; j < n && s[j] != '"'; ++j)
+					if (s[j] == '\\') ++j;
+				if (j >= n) return false;
+			}
+			else if (ch == '[' || ch == '{') ++d;
+			else if (ch == ']' || ch == '}')
+			{
+				if (d == 0) { if (ch != ']') return false; end = j; break; }
+				--d;
+			}
+			else if (ch == ',' && d == 0) starts.push_back(j + 1);
+		}
+		if (end == 0 || starts.size() < 1024) return false;
+		const size_t count = starts.size();
+		std::vector<JsonValue> items(count);
+		bool bad = false;
+#pragma omp parallel for schedule(dynamic, 512)
+		for (long k = 0; k < long(count); ++k)
+		{
+			if (bad) continue;
+			const size_t stop = size_t(k) + 1 < count ? starts[k + 1] - 1 : end; // the comma / closing bracket behind the element
+			Parser sub{ s, stop };
+			sub.i = starts[k];
+			sub.depth = depth;
+			if (!sub.value(items[k])) { bad = true; continue; }
+			sub.ws();
+			if (sub.i != stop) bad = true;
+		}
+		if (bad) return false;
+		v.kind = JsonValue::Array;
+		v.arr() = std::move(items);
+		i = end + 1;
+		--depth; // value() counted this level on entry
+		return true;
+#else
+		(void)v;
+		return false;
+#endif
+	}
+};
+
+bool Parser::value(JsonValue &v)
 	{
 		ws();
 		if (i >= n) return fail("unexpected end of input");
@@ -163,7 +229,8 @@ struct Parser
 		if (c == '{')
 		{
 			v.kind = JsonValue::Object;
-			v.obj.reserve(8);
+			auto &members = v.obj();
+			members.reserve(8);
 			++i;
 			ws();
 			if (i < n && s[i] == '}') { ++i; }
@@ -180,9 +247,9 @@ struct Parser
 					JsonValue child;
 					if (!value(child)) { ok = false; break; }
 					bool replaced = false;
-					for (auto &kv : v.obj)
+					for (auto &kv : members)
 						if (kv.first == key) { kv.second = std::move(child); replaced = true; break; }
-					if (!replaced) v.obj.emplace_back(std::move(key), std::move(child));
+					if (!replaced) members.emplace_back(std::move(key), std::move(child));
 					ws();
 					if (i < n && s[i] == ',') { ++i; continue; }
 					if (i < n && s[i] == '}') { ++i; break; }
@@ -190,10 +257,12 @@ struct Parser
 					break;
 				}
 		}
+		else if (c == '[' && parallelArray(v)) {}
 		else if (c == '[')
 		{
 			v.kind = JsonValue::Array;
-			v.arr.reserve(4);
+			auto &items = v.arr();
+			items.reserve(4);
 			++i;
 			ws();
 			if (i < n && s[i] == ']') { ++i; }
@@ -202,7 +271,7 @@ struct Parser
 				{
 					JsonValue child;
 					if (!value(child)) { ok = false; break; }
-					v.arr.push_back(std::move(child));
+					items.push_back(std::move(child));
 					ws();
 					if (i < n && s[i] == ',') { ++i; continue; }
 					if (i < n && s[i] == ']') { ++i; break; }
@@ -210,7 +279,7 @@ struct Parser
 					break;
 				}
 		}
-		else if (c == '"') { v.kind = JsonValue::String; ok = string(v.str); }
+		else if (c == '"') { v.kind = JsonValue::String; ok = string(v.str()); }
 		else if (c == '-' || (c >= '0' && c <= '9')) ok = number(v);
 		else if (n - i >= 4 && !strncmp(s + i, "true", 4)) { v.kind = JsonValue::Bool; v.b = true; i += 4; }
 		else if (n - i >= 5 && !strncmp(s + i, "false", 5)) { v.kind = JsonValue::Bool; v.b = false; i += 5; }
@@ -219,7 +288,6 @@ struct Parser
 		--depth;
 		return ok;
 	}
-};
 } // namespace
 
 bool parseJson(const std::string &text, JsonValue &out, std::string &err)

@@ -319,7 +319,7 @@ int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ign
 		p.seedHi = uint32_t(c->seed >> 32);
 		p.maxBounces = c->maxBounces;
 		p.regenLow = c->launch.regenLow > 0 ? uint32_t(c->launch.regenLow) : (c->launch.variant == 8 || c->launch.variant == 9 || c->launch.variant == 10 ? 8u : 16u);
-		p.beam = c->launch.beam < 0 ? (spp >= 256u ? 1u : 0u) : uint32_t(c->launch.beam != 0);
+		p.beam = c->launch.beam < 0 ? (spp >= 128u ? 1u : 0u) : uint32_t(c->launch.beam != 0);
 		launches = launchTrace(p, c->launch, c->stream, &usedSmem);
 	}
 	CK(cudaEventRecord(c->evStop, c->stream));

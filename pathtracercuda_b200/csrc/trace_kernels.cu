@@ -415,7 +415,7 @@ int launchTrace(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t str
 	// default: one pixel per warp (camera passes / scattered passes) for renders long enough to amortise the drain at the end of
 	// every pixel (the last paths of a pixel run with the other lanes idle: ~half a path per spp/32 samples), one pixel per lane otherwise
 	int variant = cfg.variant;
-	if (variant == 0) variant = p.spp >= 128 ? 12 : 4;
+	if (variant == 0) variant = p.spp >= 64 ? 12 : 4; // measured crossover on generated_scene: 32 spp 15.0 vs 15.2, 64 spp 15.7 vs 15.2, 128 spp 17.8 vs 15.2 Grays/s
 	switch (variant)
 	{
 	case 1: return PT_PICK(traceKernel, , 0, false);      // per-lane if/else traversal

@@ -41,7 +41,7 @@ struct LaunchConfig
 	int smCount = 148;
 	int smemScene = 1;   // stage the scene in shared memory when it fits
 	int countWork = 0;   // node/prim/shade/miss counters
-	int variant = 0;     // kernel variant (0 = default: 12 for spp >= 128, else 4.  4: one pixel per lane, while-while traversal; 1: if/else traversal;
+	int variant = 0;     // kernel variant (0 = default: 12 for spp >= 64, else 4.  4: one pixel per lane, while-while traversal; 1: if/else traversal;
 	                     //  5: + leaf parking; 8: one pixel per WARP (lanes = samples), while-while; 9/10: its other traversals;
 	                     //  12: 8 with separate passes for camera rays and scattered rays;
 	                     //  6: warp-pool wavefront, 7: CTA-pool warp-specialised wavefront - both measured slower)
@@ -51,7 +51,7 @@ struct LaunchConfig
 	int traceWarps = 0;  // wavefront: warps per CTA that only traverse (0 = half of them); the others run the other stages
 	int readyLow = -1;   // wavefront: stage warps run partial batches while the READY queue holds fewer rays than this (-1 = 128)
 	int regenLow = 0;    // see RenderParams::regenLow (0 = default)
-	int beam = -1;       // pixel beams for the camera rays of the one-pixel-per-warp kernel: 1 on, 0 off, -1 = on from 256 spp
+	int beam = -1;       // pixel beams for the camera rays of the one-pixel-per-warp kernel: 1 on, 0 off, -1 = on from 128 spp
 	int poolSlots = 0;   // CTA-pool wavefront: path slots per CTA (0 = 1280 with the scene in shared memory, 1536 without)
 	size_t maxSmemOptin = 0;
 };

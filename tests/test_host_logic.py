@@ -5,6 +5,7 @@ import json
 import os
 import re
 import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -33,6 +34,46 @@ def test_abi_exports_every_declared_symbol():
 def test_no_cpu_fallback():
     with pytest.raises(pt.PtError, match="no CUDA device"):
         pt.Pathtracer(16, 16)
+
+
+def test_large_scene_file_is_parsed_by_all_cores(tmp_path):
+    """an `objects` list of several megabytes is split at its top-level commas and parsed / converted by all cores
+    (json_min.cpp parallelArray, scene_loader.cpp): same objects, texture handles in first-use order, messages in object
+    order, the same error texts as the one-thread path"""
+    n = 20000
+    f = tmp_path / "big.json"
+    scenegen.write_synthetic_scene(str(f), n)
+    d = json.loads(f.read_text())
+    d["objects"][777]["material"]["texture"] = "b.png"
+    d["objects"][123]["material"]["texture"] = "a.png"
+    d["objects"][9000]["material"]["texture"] = "b.png"
+    d["objects"][15000]["type"] = "TORUS, [not] a {shape}"
+    d["objects"][15001]["name"] = 'brackets ] } , " in a string \\'
+    f.write_text(json.dumps(d, indent=1))
+    assert f.stat().st_size > 5 << 20
+    objs, paths, sky, cam = pt.parse_scene_file(str(f), 64, 36)
+    o2, p2, s2, c2 = pt.parse_scene_py(str(f), 64, 36)
+    assert len(objs) == n + 1 and paths == p2 and paths[:2] == ["a.png", "b.png"] and sky == s2 and bytes(cam) == bytes(c2)
+    assert all(bytes(a) == bytes(b) for a, b in zip(objs, o2))
+    assert objs[123].material.texture == 1 and objs[777].material.texture == 2 and objs[9000].material.texture == 2
+    # one thread (the sequential path) gives the same bytes
+    code = ("import sys; sys.path.insert(0, %r); import pathtracercuda_b200 as pt; o, p, s, c = pt.parse_scene_file(%r, 64, 36); "
+            "import hashlib; print(hashlib.sha1(b''.join(bytes(x) for x in o)).hexdigest(), p, s)" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(f)))
+    one = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    import hashlib
+    assert one.returncode == 0, one.stderr
+    assert one.stdout.split()[0] == hashlib.sha1(b"".join(bytes(x) for x in objs)).hexdigest()
+    # errors inside the big list: a syntax error is reported with its byte offset by the sequential path, a type error by the loader
+    text = f.read_text()
+    k = text.index('"position"', len(text) // 2)
+    f.write_text(text[:k] + '"position": [1, 2, oops],' + text[k:])
+    with pytest.raises(pt.PtError, match=r"JSON parse error at byte \d+: unexpected character"):
+        pt.parse_scene_file(str(f), 4, 4)
+    d["objects"][12000]["scale"] = [1, "two", 3]
+    d["objects"][18000]["position"] = ["x", 0, 0]
+    f.write_text(json.dumps(d))
+    with pytest.raises(pt.PtError, match='type must be number in "scale"'):
+        pt.parse_scene_file(str(f), 4, 4)
 
 
 @pytest.mark.parametrize("scene", ["cornell_box", "generated_scene"])
