@@ -331,7 +331,8 @@ def main():
             "clocks": {"sm_mhz": sm_mhz, "sm_max_mhz": clk.get("sm_max_mhz"), "reasons": sorted(clk["reasons"]), "n_samples": len(clk["samples"])},
             "roofline": {"bound": "fp32_issue", "achieved": achieved, "peak": peak_tops, "unit": "T FP32 lane-op/s", "frac": achieved / peak_tops, "traffic": traffic,
                          "note": "no dense contraction and a 64 KB on-chip scene: neither tensor nor HBM bound (DRAM traffic per launch in `traffic`, bytes). "
-                                 "achieved = algorithmic FP32 ops (SURVEY.md §8d per-unit counts x measured unit counts) / kernel time; "
+                                 "achieved = algorithmic FP32 ops (SURVEY.md §8d per-unit counts x unit counts of the plain walk from the root, from a counting launch with "
+                                 "pixel beams off - the beams skip about half of those node visits, so this counts the algorithm's work, not executed instructions) / kernel time; "
                                  f"peak = {sms} SMs x 128 lanes x {f_mhz:.0f} MHz observed under load",
                          "ops_per_ray": ops_per_ray, "units_per_ray": per_ray},
         }

@@ -130,7 +130,11 @@ const float *pt_get_hdr_mean(pt_context *ctx);
  *  "max_bounces"     path segments, default 5 (kernels/trace.cu:109)
  *  "max_leaf"        primitives per BVH leaf at most (default 4, the reference's Pathtracer.cpp:121; set before the scene)
  *  "max_global"      how many scene-spanning primitives are hoisted out of the BVH (default 8; set before the scene)
- *  "variant"         trace kernel variant, 0 = default (see csrc/trace_kernels.h LaunchConfig) */
+ *  "variant"         trace kernel variant, 0 = default (see csrc/trace_kernels.h LaunchConfig)
+ *  "beam"            pixel beams for camera rays (one-pixel-per-warp kernels): 1 on, 0 off, -1 auto (default: on from 128 spp)
+ *  "regen_low"       one-pixel-per-warp kernels: idle lanes wait until this many can start new samples together (0 = default)
+ *  "tex_unit"        1 (default): texture taps through CUDA texture objects, as the reference (Pathtracer.cpp:259-288);
+ *                    0: fp32 bilinear filter in software over the packed texels */
 int pt_set_option(pt_context *ctx, const char *key, double value);
 int pt_get_stats(const pt_context *ctx, pt_stats *out);
 

@@ -74,6 +74,11 @@ def test_pixel_beam_lists_do_not_change_the_image(scene, W, H):
     pixels, entries, overflows, longest = E.beam_stats
     assert ra == rb and np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert pixels == W * H and overflows == 0 and longest <= 16 and entries > 0
+    if scene == "generated_scene":
+        # pixels so large that their beams reach more than 16 leaves: those fall back to the walk from the root
+        a, ra = E.render(cam, 16, 9, 24)
+        b, rb = E.render(cam, 16, 9, 24, beam=True)
+        assert E.beam_stats[2] > 0 and ra == rb and np.array_equal(a.view(np.uint32), b.view(np.uint32))
 
 
 def test_quirks_match_oracle():

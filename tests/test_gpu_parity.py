@@ -183,6 +183,15 @@ def test_kernel_variants_bit_identical():
     # pixel beams (camera rays take their leaves from the pixel's list instead of walking the tree): same closest hits
     assert np.array_equal(bits(run(8, 80, beam=1)), bits(run(8, 80, beam=0)))
     assert np.array_equal(bits(run(12, 80, beam=1)), bits(run(12, 80, beam=0)))
+    # pixels so large that their beams reach more than 16 leaves (those fall back to the walk from the root)
+    def coarse(beam):
+        with pt.Pathtracer(16, 9) as P:
+            cam = P.loadSceneFile(f"{pt.ASSETS}/scenes/generated_scene.json", cwd=pt.ASSETS)
+            P.setOption("variant", 12)
+            P.setOption("beam", beam)
+            P.render(cam, 96, True)
+            return P.getHDRMean()
+    assert np.array_equal(bits(coarse(1)), bits(coarse(0)))
     assert np.array_equal(bits(run(0, 256)), bits(run(12, 256, beam=0)))
     assert np.allclose(run(8, 5), run(4, 5), rtol=2e-5, atol=1e-7)  # fewer samples than lanes
     with pt.Pathtracer(320, 180) as P:  # shared-memory scene vs global-memory scene
