@@ -34,8 +34,8 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 	if constexpr (SMEM)
 	{
 		stageSceneToSmem(smemScene, p.scene.sceneBlob, (p.scene.nodeCount + p.scene.primCount) * 64u, &mbar);
-		sv.nodes = smemScene;
-		sv.prims = smemScene + size_t(p.scene.nodeCount) * 4;
+		sv.nodes = smemWindow(smemScene);
+		sv.prims = sv.nodes + size_t(p.scene.nodeCount) * 4;
 		sv.globalCount = p.scene.globalCount;
 	}
 	else

@@ -68,8 +68,8 @@ __global__ void __launch_bounds__(kPoolThreads, 1) traceKernelWP(const RenderPar
 	if constexpr (SMEM)
 	{
 		stageSceneToSmem(smemScene, p.scene.sceneBlob, (p.scene.nodeCount + p.scene.primCount) * 64u, &mbar);
-		sv.nodes = smemScene;
-		sv.prims = smemScene + size_t(p.scene.nodeCount) * 4;
+		sv.nodes = smemWindow(smemScene);
+		sv.prims = sv.nodes + size_t(p.scene.nodeCount) * 4;
 	}
 	else
 	{

@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(kWfThreads, 1) traceKernelWF(const RenderParam
 	if constexpr (SMEM)
 	{
 		stageSceneToSmem(smemScene, p.scene.sceneBlob, (p.scene.nodeCount + p.scene.primCount) * 64u, &mbar);
-		sv.nodes = smemScene;
-		sv.prims = smemScene + size_t(p.scene.nodeCount) * 4;
+		sv.nodes = smemWindow(smemScene);
+		sv.prims = sv.nodes + size_t(p.scene.nodeCount) * 4;
 	}
 	else
 	{
