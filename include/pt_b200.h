@@ -138,6 +138,13 @@ const float *pt_get_hdr_mean(pt_context *ctx);
 int pt_set_option(pt_context *ctx, const char *key, double value);
 int pt_get_stats(const pt_context *ctx, pt_stats *out);
 
+/* Camera::rotate(pitch, yaw, roll) / Camera::translate(x, y, z)   Camera.h:10-11, Camera.inl:30-52 (the reference's
+ * interactive controls, main.cpp:404-420).  Host-only helpers on the POD camera: angles in radians, pitch about the
+ * camera's right axis, yaw about the world up axis, roll ignored (as in the reference); the translation is along the camera's
+ * right / up / backward axes.  The next pt_render with the changed camera should pass ignore_history = 1. */
+void pt_camera_rotate(pt_camera_desc *camera, float pitch, float yaw, float roll);
+void pt_camera_translate(pt_camera_desc *camera, float x, float y, float z);
+
 /* Deterministic primary-ray pass (parity gate): pixel-centre rays u=(x+0.5)/W, v=(y+0.5)/H, t_min=0.001; writes the
  * scene-order object index (or -1) and hit t (0 on miss) per pixel into HOST buffers of W*H elements. */
 int pt_primary_pass(pt_context *ctx, const pt_camera_desc *camera, int32_t *hit_index, float *hit_t);

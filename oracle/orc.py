@@ -194,6 +194,12 @@ class RefHost:
         self.L.refh_get_camera(_p(out))
         return out
 
+    def camera_rotate(self, pitch, yaw, roll=0.0):
+        self.L.refh_camera_rotate(C.c_float(pitch), C.c_float(yaw), C.c_float(roll))
+
+    def camera_translate(self, x, y, z):
+        self.L.refh_camera_translate(C.c_float(x), C.c_float(y), C.c_float(z))
+
     def textures(self):
         return [self.L.refh_texture_path(i).decode() for i in range(self.L.refh_texture_count())], self.L.refh_skybox_handle()
 

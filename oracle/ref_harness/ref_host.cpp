@@ -225,6 +225,9 @@ extern "C"
 		// m_tanHalfFovy, m_aspectRatio, origin, lowerLeft, horizontal, vertical, right, up, backward
 		memcpy(out23, &g_camera, sizeof(float) * 23);
 	}
+	// the reference's own interactive camera controls (Camera.inl:30-52) on the current camera
+	void refh_camera_rotate(float pitch, float yaw, float roll) { g_camera.rotate(pitch, yaw, roll); }
+	void refh_camera_translate(float x, float y, float z) { g_camera.translate(x, y, z); }
 	int refh_texture_count() { return (int)g_refCapture.texturePaths.size(); }
 	const char *refh_texture_path(int i) { return g_refCapture.texturePaths[i].c_str(); }
 	uint32_t refh_skybox_handle() { return g_refCapture.skybox; }

@@ -38,6 +38,8 @@ def load_library():
         "pt_get_ldr": (vp, [vp]),
         "pt_set_option": (i32, [vp, cp, C.c_double]),
         "pt_get_stats": (i32, [vp, vp]),
+        "pt_camera_rotate": (None, [vp, f32, f32, f32]),
+        "pt_camera_translate": (None, [vp, f32, f32, f32]),
         "pt_primary_pass": (i32, [vp, vp, vp, vp]),
         "pt_trace_rays": (i32, [vp, sz, vp, vp, f32, vp, vp, vp]),
         "pt_accum_device_ptr": (vp, [vp]),
@@ -60,7 +62,7 @@ def load_library():
 
 
 EXPORTS = ["pt_create", "pt_destroy", "pt_set_scene", "pt_load_texture", "pt_load_texture_mem", "pt_set_skybox", "pt_render",
-           "pt_get_timing_ms", "pt_get_hdr", "pt_get_hdr_mean", "pt_get_ldr", "pt_set_option", "pt_get_stats", "pt_primary_pass",
+           "pt_get_timing_ms", "pt_get_hdr", "pt_get_hdr_mean", "pt_get_ldr", "pt_set_option", "pt_get_stats", "pt_camera_rotate", "pt_camera_translate", "pt_primary_pass",
            "pt_trace_rays", "pt_accum_device_ptr", "pt_set_accum_device_ptr", "pt_load_scene_file", "pt_parse_scene_file",
            "pt_write_png", "pt_write_hdr", "pt_read_image", "pt_free", "pt_last_error", "pt_version"]
 
@@ -76,6 +78,18 @@ def _check(L, rc, what):
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def camera_rotate(cam, pitch, yaw, roll=0.0):
+    """Camera::rotate (reference Camera.inl:30-48) on a pt_camera_desc, in place; radians"""
+    load_library().pt_camera_rotate(C.byref(cam), pitch, yaw, roll)
+    return cam
+
+
+def camera_translate(cam, x, y, z):
+    """Camera::translate (reference Camera.inl:50-52) on a pt_camera_desc, in place; along the camera's right / up / backward axes"""
+    load_library().pt_camera_translate(C.byref(cam), x, y, z)
+    return cam
 
 
 def parse_scene_file(path, width, height, capacity=None):

@@ -438,6 +438,15 @@ int pt_get_stats(const pt_context *c, pt_stats *out)
 	return PT_OK;
 }
 
+void pt_camera_rotate(pt_camera_desc *camera, float pitch, float yaw, float roll)
+{
+	if (camera) cameraRotate(*camera, pitch, yaw, roll);
+}
+void pt_camera_translate(pt_camera_desc *camera, float x, float y, float z)
+{
+	if (camera) cameraTranslate(*camera, x, y, z);
+}
+
 int pt_primary_pass(pt_context *c, const pt_camera_desc *camera, int32_t *hit_index, float *hit_t)
 {
 	if (!c || !camera || !hit_index || !hit_t) return setError(PT_E_INVALID, "pt_primary_pass: bad arguments");

@@ -112,6 +112,58 @@ void computeCamera(const pt_camera_desc &c, CameraDev &out)
 	}
 }
 
+namespace
+{
+struct CamBasis { V3 origin, right, up, backward; };
+V3 v3add(V3 a, V3 b) { return V3{ a.x + b.x, a.y + b.y, a.z + b.z }; }
+V3 v3scale(V3 a, float s) { return V3{ a.x * s, a.y * s, a.z * s }; }
+V3 v3cross(V3 u, V3 v) { return V3{ u.y * v.z - u.z * v.y, u.z * v.x - u.x * v.z, u.x * v.y - u.y * v.x }; }
+float v3dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+V3 v3norm(V3 v) { const float inv = 1.0f / sqrtf(v3dot(v, v)); return V3{ inv * v.x, inv * v.y, inv * v.z }; }
+CamBasis basisOf(const pt_camera_desc &c)
+{
+	CamBasis b;
+	b.origin = V3{ c.position[0], c.position[1], c.position[2] };
+	b.backward = v3norm(V3{ b.origin.x - c.look_at[0], b.origin.y - c.look_at[1], b.origin.z - c.look_at[2] }); // Camera.inl:18-20
+	b.right = v3norm(v3cross(V3{ c.up[0], c.up[1], c.up[2] }, b.backward));
+	b.up = v3cross(b.backward, b.right);
+	return b;
+}
+void writeBack(pt_camera_desc &c, const CamBasis &b)
+{
+	c.position[0] = b.origin.x; c.position[1] = b.origin.y; c.position[2] = b.origin.z;
+	c.look_at[0] = b.origin.x - b.backward.x; c.look_at[1] = b.origin.y - b.backward.y; c.look_at[2] = b.origin.z - b.backward.z;
+	c.up[0] = b.up.x; c.up[1] = b.up.y; c.up[2] = b.up.z;
+}
+// rotateAroundVector, vec3.inl:184-187 (Rodrigues)
+V3 rotateAround(V3 v, V3 axis, float cosA, float sinA)
+{
+	return v3add(v3add(v3scale(v, cosA), v3scale(v3cross(axis, v), sinA)), v3scale(v3scale(axis, v3dot(axis, v)), 1.0f - cosA));
+}
+} // namespace
+
+void cameraRotate(pt_camera_desc &c, float pitch, float yaw, float roll)
+{
+	(void)roll; // the reference takes the argument and ignores it (Camera.inl:30-48)
+	CamBasis b = basisOf(c);
+	const float cosPitch = cosf(-pitch), sinPitch = sinf(-pitch); // around the local x axis
+	b.up = rotateAround(b.up, b.right, cosPitch, sinPitch);
+	b.backward = rotateAround(b.backward, b.right, cosPitch, sinPitch);
+	const float cosYaw = cosf(-yaw), sinYaw = sinf(-yaw); // around the world up axis
+	const V3 worldUp = { 0.0f, 1.0f, 0.0f };
+	b.right = rotateAround(b.right, worldUp, cosYaw, sinYaw);
+	b.up = rotateAround(b.up, worldUp, cosYaw, sinYaw);
+	b.backward = rotateAround(b.backward, worldUp, cosYaw, sinYaw);
+	writeBack(c, b);
+}
+
+void cameraTranslate(pt_camera_desc &c, float x, float y, float z)
+{
+	CamBasis b = basisOf(c);
+	b.origin = v3add(b.origin, v3add(v3add(v3scale(b.right, x), v3scale(b.up, y)), v3scale(b.backward, z))); // Camera.inl:50
+	writeBack(c, b);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // BVH build
 // ---------------------------------------------------------------------------------------------------------------

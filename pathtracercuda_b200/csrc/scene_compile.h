@@ -39,5 +39,10 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 
 // Camera ctor + update() equivalent (reference Camera.inl:4-23,54-62)
 void computeCamera(const pt_camera_desc &c, CameraDev &out);
+// Camera::rotate / Camera::translate (reference Camera.inl:30-52) on the POD camera: the basis (right, up, backward) is
+// rebuilt from the description as the ctor does, moved as the reference moves it, and written back as
+// look_at = position - backward, up = the new up vector (the ctor then reproduces the same basis).
+void cameraRotate(pt_camera_desc &c, float pitch, float yaw, float roll);
+void cameraTranslate(pt_camera_desc &c, float x, float y, float z);
 
 } // namespace ptb
