@@ -36,6 +36,29 @@ def test_no_cpu_fallback():
         pt.Pathtracer(16, 16)
 
 
+def test_camera_controls_match_reference():
+    """pt_camera_rotate / pt_camera_translate against the reference's own Camera::rotate / translate (Camera.inl:30-52,
+    fixture from tools/make_golden_camera.py): after every move of a 24-move walk the camera rebuilt from our description
+    has the reference's origin, image-plane vectors and basis (the description round-trips the basis, so a few ulp per move)"""
+    d = load_golden("camera_moves")
+    for k in range(d["start"].shape[0]):
+        from pathtracercuda_b200.abi import CameraDesc
+        cam = CameraDesc.from_buffer_copy(bytes(d["start"][k]))
+        O = orc.Oracle([pt.make_object("SPHERE")])
+        for m, ref in zip(d["moves"][k], d["states"][k][1:]):
+            if m[0] == 0:
+                pt.camera_rotate(cam, float(m[1]), float(m[2]), float(m[3]))
+            else:
+                pt.camera_translate(cam, float(m[1]), float(m[2]), float(m[3]))
+            origin, ll, hor, ver = ref[2:5], ref[5:8], ref[8:11], ref[11:14]
+            assert np.allclose(np.array(cam.position), origin, rtol=0, atol=2e-5)
+            for s_, t_ in [(0.0, 0.0), (1.0, 0.0), (0.0, 1.0), (0.5, 0.5), (0.9, 0.2)]:
+                ray = O.camera_ray(cam, s_, t_)  # Camera ctor + getRay on OUR description
+                v = ll + np.float32(s_) * hor + np.float32(t_) * ver
+                assert np.allclose(ray[3:], v / np.linalg.norm(v), rtol=0, atol=5e-6), (k, m)
+        assert not np.allclose(np.array(cam.position), d["states"][k][0][2:5])  # the walk went somewhere
+
+
 def test_large_scene_file_is_parsed_by_all_cores(tmp_path):
     """an `objects` list of several megabytes is split at its top-level commas and parsed / converted by all cores
     (json_min.cpp parallelArray, scene_loader.cpp): same objects, texture handles in first-use order, messages in object
