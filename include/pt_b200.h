@@ -133,6 +133,8 @@ const float *pt_get_hdr_mean(pt_context *ctx);
  *  "variant"         trace kernel variant, 0 = default (see csrc/trace_kernels.h LaunchConfig)
  *  "beam"            pixel beams for camera rays (one-pixel-per-warp kernels): 1 on, 0 off, -1 auto (default: on from 128 spp)
  *  "regen_low"       one-pixel-per-warp kernels: idle lanes wait until this many can start new samples together (0 = default)
+ *  "sort_samples"    one-pixel-per-warp kernels: hand a pixel's samples out in the order of their first scattering direction
+ *                    (an order only: same Philox counters, same paths): 1 on, 0 off, -1 auto (default: on from 1024 spp)
  *  "tex_unit"        1 (default): texture taps through CUDA texture objects, as the reference (Pathtracer.cpp:259-288);
  *                    0: fp32 bilinear filter in software over the packed texels */
 int pt_set_option(pt_context *ctx, const char *key, double value);

@@ -23,6 +23,84 @@ namespace ptb
 {
 
 // ---------------------------------------------------------------------------------------------------------------
+// Sample order.  The lanes of a warp trace samples of one pixel; the scattered rays of the first bounce leave (nearly) the
+// same point, in directions set by the sample's first two BSDF randoms.  Handing the samples out in the order of those
+// randoms - 32..256 bins: lobe + azimuth (the top bits of the first), polar angle (the top bits of the second), neighbours adjacent -
+// puts similar directions into the same pass: similar walks, the same leaves, the same hit-or-miss outcome, the same lobe.
+// It is only an order: every sample is still drawn from its own Philox counter, so the estimator and the set of paths are
+// unchanged (the image differs by float summation order alone).  A counting sort by the warp, once per pixel: pass A
+// draws each sample's randoms and counts the bins, pass B gives every sample its place (stable, no atomics: ranks
+// come from match_any, so the order is the same from run to run).  `order` and `keys` live in global scratch (L2).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSortBinsMax = 256; // bins = 2^(bitsA + bitsB) <= 256, >= 32
+static __device__ __noinline__ void sortSamples(uint32_t pixel, uint32_t spp, uint32_t sampleOffset, uint32_t sampleStride, uint32_t seedLo, uint32_t seedHi,
+                                                uint32_t bitsA, uint32_t bitsB, uint16_t *order, uint16_t *keys, uint16_t *hist)
+{
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t lt = (1u << lane) - 1u;
+	const uint32_t bins = 1u << ((bitsA & 15u) + bitsB), perLane = bins >> 5;
+	for (uint32_t k = lane; k < bins; k += 32) hist[k] = 0;
+	__syncwarp();
+	// pass A: keys + histogram
+	for (uint32_t base = 0; base < spp; base += 32)
+	{
+		const uint32_t s = base + lane;
+		uint32_t key = bins; // lanes past the end: a bin of their own, never counted
+		if (s < spp)
+		{
+			const uint4 r = philoxNI(pixel, sampleOffset + s * sampleStride, 0u, seedLo, seedHi);
+			const uint32_t a = r.z >> (32u - (bitsA & 15u)), b = bitsB ? r.w >> (32u - bitsB) : 0u;
+			// snake through the minor bins: neighbouring keys are neighbouring directions
+			if (bitsA & 16u) { const uint32_t nb = bitsA & 15u; const uint32_t a2 = r.z >> (32u - nb); key = (b << nb) | ((b & 1u) ? ((1u << nb) - 1u) - a2 : a2); }
+			else key = (a << bitsB) | ((a & 1u) ? ((1u << bitsB) - 1u) - b : b);
+			keys[s] = uint16_t(key);
+		}
+		const uint32_t same = __match_any_sync(0xffffffffu, key);
+		if (key < bins && (same & lt) == 0u) hist[key] = uint16_t(hist[key] + __popc(same)); // the first lane of each group
+		__syncwarp();
+	}
+	// counts -> first position of every bin (lane l owns bins l * perLane ... + perLane - 1)
+	{
+		uint32_t sum = 0;
+		for (uint32_t k = 0; k < perLane; ++k) sum += hist[lane * perLane + k];
+		uint32_t incl = sum;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (int(lane) >= o) incl += t;
+		}
+		uint32_t run = incl - sum;
+		__syncwarp();
+		for (uint32_t k = 0; k < perLane; ++k)
+		{
+			const uint32_t c = hist[lane * perLane + k];
+			hist[lane * perLane + k] = uint16_t(run);
+			run += c;
+		}
+		__syncwarp();
+	}
+	// pass B: places (stable within a bin: batches in order, lanes in order)
+	for (uint32_t base = 0; base < spp; base += 32)
+	{
+		const uint32_t s = base + lane;
+		const uint32_t key = s < spp ? uint32_t(__ldcg(keys + s)) : bins;
+		const uint32_t same = __match_any_sync(0xffffffffu, key);
+		uint32_t first = 0;
+		if (key < bins) first = hist[key];
+		__syncwarp();
+		if (key < bins)
+		{
+			order[first + uint32_t(__popc(same & lt))] = uint16_t(s);
+			if ((same & lt) == 0u) hist[key] = uint16_t(first + __popc(same));
+		}
+		__syncwarp();
+	}
+	__threadfence_block();
+	__syncwarp();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // the trace kernel
 // ---------------------------------------------------------------------------------------------------------------
 template <bool SMEM, bool COUNT, int TRAV, bool SHARE, bool SPLIT = false>
@@ -48,6 +126,9 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 	// SHARE: the leaves the camera rays of the warp's pixel can reach (beamLeaves), nearest first
 	__shared__ BeamEntry beamList[SHARE && TRAV >= 1 ? kTraceThreads / 32 : 1][kBeamMax];
 	int nBeam = -1;
+	// SPLIT: per-warp bin counters of sortSamples, and the warp's slice of the sample-order scratch
+	__shared__ uint16_t sortHist[SPLIT ? kTraceThreads / 32 : 1][SPLIT ? kSortBinsMax : 1];
+	const uint16_t *sampleOrder = nullptr;
 
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t totalPixels = p.width * p.height;
@@ -82,7 +163,13 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 				if (pixel != kInvalid && wNext < p.spp && (uint32_t(__popc(needMask)) >= p.regenLow || needMask == 0xffffffffu || p.spp - wNext < 32u))
 				{
 					const uint32_t mine = wNext + __popc(needMask & ((1u << lane) - 1u));
-					if (!alive && mine < p.spp) { sample = mine; generate = true; }
+					if (!alive && mine < p.spp)
+					{
+						sample = mine;
+						if constexpr (SPLIT)
+							if (sampleOrder != nullptr) sample = __ldcg(sampleOrder + mine); // the pixel's samples in the order of their first scattering direction
+						generate = true;
+					}
 					wNext = min(p.spp, wNext + uint32_t(__popc(needMask)));
 				}
 				if (!__any_sync(0xffffffffu, alive || generate))
@@ -115,6 +202,15 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 					if (next >= totalPixels) break;
 					pixel = uint32_t(next);
 					wNext = 0;
+					if constexpr (SPLIT)
+					{
+						if (p.sortScratch != nullptr)
+						{
+							uint16_t *mine = p.sortScratch + (size_t(blockIdx.x) * (kTraceThreads / 32) + (threadIdx.x >> 5)) * 2u * p.sortStride;
+							sortSamples(pixel, p.spp, p.sampleOffset, p.sampleStride, p.seedLo, p.seedHi, p.sortBitsA, p.sortBitsB, mine, mine + p.sortStride, sortHist[threadIdx.x >> 5]);
+							sampleOrder = mine;
+						}
+					}
 					if constexpr (TRAV >= 1)
 					{
 						if (p.beam)
@@ -406,7 +502,7 @@ int launchTrace(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t str
 	}
 	const size_t sceneBytes = (size_t(p.scene.nodeCount) + p.scene.primCount) * 64;
 	// leave room for 2+ CTAs per SM when the scene is small; a scene larger than the opt-in limit stays in L2/HBM
-	const bool smem = cfg.smemScene && sceneBytes + 8192 <= cfg.maxSmemOptin; // static shared memory: barrier + beam lists
+	const bool smem = cfg.smemScene && sceneBytes + 24576 <= cfg.maxSmemOptin; // static shared memory: barrier + beam lists + sort counters
 	if (usedSmem) *usedSmem = smem ? 1 : 0;
 	const size_t sb = smem ? sceneBytes : 0;
 #define PT_PICK(KERN, ...)                                                                                                        \

@@ -33,6 +33,11 @@ struct RenderParams
 	uint32_t seedLo, seedHi;
 	uint32_t maxBounces;
 	uint32_t regenLow = 1; // one-pixel-per-warp kernel: idle lanes wait until this many can start new samples together
+	// one-pixel-per-warp kernel: the samples of a pixel are handed out in the order of their first scattering direction
+	// (sortSamples, trace_kernels.cu).  sortScratch = 2 x sortStride uint16 per warp of the grid; 0 = samples in index order
+	uint16_t *sortScratch = nullptr;
+	uint32_t sortStride = 0;
+	uint32_t sortBitsA = 4, sortBitsB = 2; // bins of the first / second random (2^(A+B) bins, 32..256)
 	uint32_t beam = 0;     // one-pixel-per-warp kernel: camera rays take their leaves from the pixel's beam list (trace_device.cuh)
 };
 
@@ -51,6 +56,8 @@ struct LaunchConfig
 	int traceWarps = 0;  // wavefront: warps per CTA that only traverse (0 = half of them); the others run the other stages
 	int readyLow = -1;   // wavefront: stage warps run partial batches while the READY queue holds fewer rays than this (-1 = 128)
 	int regenLow = 0;    // see RenderParams::regenLow (0 = default)
+	int sortBitsA = 0, sortBitsB = -1; // 0 / -1 = defaults
+	int sortSamples = -1; // order a pixel's samples by first scattering direction: 1 on, 0 off, -1 = on from 1024 spp (and spp <= 65535)
 	int beam = -1;       // pixel beams for the camera rays of the one-pixel-per-warp kernel: 1 on, 0 off, -1 = on from 128 spp
 	int poolSlots = 0;   // CTA-pool wavefront: path slots per CTA (0 = 1280 with the scene in shared memory, 1536 without)
 	size_t maxSmemOptin = 0;

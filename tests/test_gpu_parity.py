@@ -287,6 +287,30 @@ def test_textures_and_skybox():
     assert (rel.max(-1) > 2e-3).mean() < 0.03 and abs(a[..., :3].mean() / b[..., :3].mean() - 1) < 2e-3
 
 
+def test_sample_order_changes_nothing_but_the_order():
+    """long renders hand a pixel's samples to the lanes in the order of their first scattering direction (sortSamples):
+    the same Philox counters, so the same paths and ray count; the image differs by float summation order only and is
+    the same from run to run; also with a sample partition (offset / stride) and when accumulating onto an earlier render"""
+    def run(sort, **opts):
+        with pt.Pathtracer(160, 90) as P:
+            cam = P.loadSceneFile(f"{pt.ASSETS}/scenes/generated_scene.json", cwd=pt.ASSETS)
+            P.setOption("sort_samples", sort)
+            for k, v in opts.items():
+                P.setOption(k, v)
+            P.render(cam, 1056, True)   # not a multiple of 32 on purpose... 1056 = 33 x 32; and a ragged second call
+            P.render(cam, 1031, False)
+            return P.getHDRMean(), P.stats().rays
+    a, ra = run(0)
+    b, rb = run(1)
+    c, rc = run(1)
+    assert ra == rb == rc and np.array_equal(bits(b), bits(c))
+    assert not np.array_equal(bits(a), bits(b)) and np.allclose(a, b, rtol=3e-5, atol=1e-7)
+    a2, r2 = run(0, sample_offset=3, sample_stride=4)
+    b2, r3 = run(1, sample_offset=3, sample_stride=4)
+    assert r2 == r3 and np.allclose(a2, b2, rtol=3e-5, atol=1e-7) and not np.allclose(a, a2, rtol=1e-3)
+    assert np.allclose(run(1, sort_bits_a=5, sort_bits_b=3)[0], a, rtol=3e-5, atol=1e-7)
+
+
 def test_texture_unit_matches_software_filter():
     """texture taps through the texture unit (one TEX instruction, 1.8 fixed-point filter weights - the reference's own
     path) against the fp32 software filter over the packed texels (option tex_unit=0): same image up to the weights'
