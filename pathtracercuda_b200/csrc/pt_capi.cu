@@ -329,9 +329,9 @@ int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ign
 			p.sortStride = 0;
 			if (wantSort)
 			{
-				const uint32_t stride = (spp + 31u) & ~31u;
+				const uint32_t stride = (spp + 127u) & ~127u;
 				const size_t warps = size_t(c->launch.smCount) * 2u * (1024u / 32u); // launchKernel: smCount x blocksPerSm (<= 2) CTAs of 32 warps
-				const size_t bytes = warps * 2u * stride * sizeof(uint16_t);
+				const size_t bytes = warps * size_t(stride) * (2u + 2u);             // order + keys per sample (sortSamples)
 				if (bytes > c->sortScratchBytes)
 				{
 					if (c->sortScratch) CK(cudaFree(c->sortScratch));
@@ -342,6 +342,7 @@ int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ign
 				}
 				p.sortScratch = static_cast<uint16_t *>(c->sortScratch);
 				p.sortStride = stride;
+				p.sortIgnore = c->launch.sortSamples == 2 ? 1u : 0u;
 				// measured on generated_scene (ms per 4096 spp): 64 bins 576, 128 bins (4 + 3 bits) 569, 256 bins 570-573; 2048 spp: 297 / 295
 				p.sortBitsA = c->launch.sortBitsA > 0 ? uint32_t(c->launch.sortBitsA) : 4u;
 				p.sortBitsB = c->launch.sortBitsB >= 0 ? uint32_t(c->launch.sortBitsB) : (spp >= 2048u ? 3u : 2u);
@@ -349,7 +350,7 @@ int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ign
 					const uint32_t major = p.sortBitsA & 16u;
 					uint32_t a = p.sortBitsA & 15u, b = p.sortBitsB;
 					if (a + b < 5u) a = 5u - b;
-					if (a + b > 8u) { a = 5u; b = 3u; }
+					if (a + b > 7u) { a = 4u; b = 3u; }
 					p.sortBitsA = a | major;
 					p.sortBitsB = b;
 				}

@@ -29,36 +29,59 @@ namespace ptb
 // puts similar directions into the same pass: similar walks, the same leaves, the same hit-or-miss outcome, the same lobe.
 // It is only an order: every sample is still drawn from its own Philox counter, so the estimator and the set of paths are
 // unchanged (the image differs by float summation order alone).  A counting sort by the warp, once per pixel: pass A
-// draws each sample's randoms and counts the bins, pass B gives every sample its place (stable, no atomics: ranks
-// come from match_any, so the order is the same from run to run).  `order` and `keys` live in global scratch (L2).
+// draws each sample's randoms and counts the bins (shared-memory atomics: only the counts are used), pass B gives every
+// sample its place (ranks from match_any, not from atomics, so the order is the same from run to run).  `order` and `keys` live in global scratch (L2).
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kSortBinsMax = 256; // bins = 2^(bitsA + bitsB) <= 256, >= 32
-static __device__ __noinline__ void sortSamples(uint32_t pixel, uint32_t spp, uint32_t sampleOffset, uint32_t sampleStride, uint32_t seedLo, uint32_t seedHi,
-                                                uint32_t bitsA, uint32_t bitsB, uint16_t *order, uint16_t *keys, uint16_t *hist)
+constexpr int kSortBinsMax = 128; // bins = 2^(bitsA + bitsB) <= 128, >= 32
+// Scratch of one warp (global memory, L2): order[stride] uint16 | keys[stride] uint16.  Four samples per lane and iteration
+// (s = base + 4 * lane + k): the four Philox evaluations are independent, the key loads and stores are vectors.
+// (Keeping the draws too, so that generating the camera ray reads slot 0 back instead of drawing it again, was measured:
+// 634 vs 574 ms - a dependent 16-byte gather from a 300 MB scratch at the head of every camera pass.)
+static __device__ __forceinline__ size_t sortScratchBytesPerWarp(uint32_t stride) { return size_t(stride) * (2u + 2u); }
+static __device__ __forceinline__ char *sortScratchOfWarp(const RenderParams &p)
 {
+	return reinterpret_cast<char *>(p.sortScratch) + (size_t(blockIdx.x) * (kTraceThreads / 32) + (threadIdx.x >> 5)) * sortScratchBytesPerWarp(p.sortStride);
+}
+// (two arguments on purpose: the call sits in the kernel's main loop, and every argument register is one the loop loses)
+static __device__ __noinline__ void sortSamples(uint32_t pixel, const RenderParams *pp, uint32_t *hist)
+{
+	const RenderParams &p = *pp;
+	const uint32_t spp = p.spp, sampleOffset = p.sampleOffset, sampleStride = p.sampleStride, seedLo = p.seedLo, seedHi = p.seedHi;
+	const uint32_t bitsA = p.sortBitsA, bitsB = p.sortBitsB;
+	char *mine = sortScratchOfWarp(p);
+	uint16_t *order = reinterpret_cast<uint16_t *>(mine);
+	uint16_t *keys = order + p.sortStride;
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t lt = (1u << lane) - 1u;
-	const uint32_t bins = 1u << ((bitsA & 15u) + bitsB), perLane = bins >> 5;
+	const uint32_t nbA = bitsA & 15u;
+	const uint32_t bins = 1u << (nbA + bitsB), perLane = bins >> 5;
 	for (uint32_t k = lane; k < bins; k += 32) hist[k] = 0;
 	__syncwarp();
-	// pass A: keys + histogram
-	for (uint32_t base = 0; base < spp; base += 32)
+	// pass A: draws, keys, histogram
+	for (uint32_t base = 0; base < spp; base += 128)
 	{
-		const uint32_t s = base + lane;
-		uint32_t key = bins; // lanes past the end: a bin of their own, never counted
-		if (s < spp)
+		const uint32_t s0 = base + 4u * lane;
+		uint32_t key[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
 		{
-			const uint4 r = philoxNI(pixel, sampleOffset + s * sampleStride, 0u, seedLo, seedHi);
-			const uint32_t a = r.z >> (32u - (bitsA & 15u)), b = bitsB ? r.w >> (32u - bitsB) : 0u;
-			// snake through the minor bins: neighbouring keys are neighbouring directions
-			if (bitsA & 16u) { const uint32_t nb = bitsA & 15u; const uint32_t a2 = r.z >> (32u - nb); key = (b << nb) | ((b & 1u) ? ((1u << nb) - 1u) - a2 : a2); }
-			else key = (a << bitsB) | ((a & 1u) ? ((1u << bitsB) - 1u) - b : b);
-			keys[s] = uint16_t(key);
+			const uint32_t s = s0 + uint32_t(k);
+			key[k] = bins; // samples past the end: a bin of their own, never counted
+			if (s < spp)
+			{
+				const uint4 r = philox4x32_10(pixel, sampleOffset + s * sampleStride, 0u, 0u, seedLo, seedHi);
+				const uint32_t a = r.z >> (32u - nbA), bb = bitsB ? r.w >> (32u - bitsB) : 0u;
+				// snake through the minor bins: neighbouring keys are neighbouring directions
+				if (bitsA & 16u) key[k] = (bb << nbA) | ((bb & 1u) ? ((1u << nbA) - 1u) - a : a);
+				else key[k] = (a << bitsB) | ((a & 1u) ? ((1u << bitsB) - 1u) - bb : bb);
+			}
 		}
-		const uint32_t same = __match_any_sync(0xffffffffu, key);
-		if (key < bins && (same & lt) == 0u) hist[key] = uint16_t(hist[key] + __popc(same)); // the first lane of each group
-		__syncwarp();
+		if (s0 < spp) __stcg(reinterpret_cast<uint2 *>(keys + s0), make_uint2(key[0] | (key[1] << 16), key[2] | (key[3] << 16))); // stride is a multiple of 128
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
+			if (key[k] < bins) atomicAdd(&hist[key[k]], 1u); // only the COUNTS are used: no order dependence
 	}
+	__syncwarp();
 	// counts -> first position of every bin (lane l owns bins l * perLane ... + perLane - 1)
 	{
 		uint32_t sum = 0;
@@ -75,26 +98,32 @@ static __device__ __noinline__ void sortSamples(uint32_t pixel, uint32_t spp, ui
 		for (uint32_t k = 0; k < perLane; ++k)
 		{
 			const uint32_t c = hist[lane * perLane + k];
-			hist[lane * perLane + k] = uint16_t(run);
+			hist[lane * perLane + k] = run;
 			run += c;
 		}
 		__syncwarp();
 	}
-	// pass B: places (stable within a bin: batches in order, lanes in order)
-	for (uint32_t base = 0; base < spp; base += 32)
+	// pass B: places.  Stable in the order (k, lane) within a 128-sample batch - any fixed order will do, it is the same from run to run
+	for (uint32_t base = 0; base < spp; base += 128)
 	{
-		const uint32_t s = base + lane;
-		const uint32_t key = s < spp ? uint32_t(__ldcg(keys + s)) : bins;
-		const uint32_t same = __match_any_sync(0xffffffffu, key);
-		uint32_t first = 0;
-		if (key < bins) first = hist[key];
-		__syncwarp();
-		if (key < bins)
+		const uint32_t s0 = base + 4u * lane;
+		uint2 packed = make_uint2(bins | (bins << 16), bins | (bins << 16));
+		if (s0 < spp) packed = __ldcg(reinterpret_cast<const uint2 *>(keys + s0));
+		const uint32_t key[4] = { packed.x & 0xffffu, packed.x >> 16, packed.y & 0xffffu, packed.y >> 16 };
+#pragma unroll
+		for (int k = 0; k < 4; ++k)
 		{
-			order[first + uint32_t(__popc(same & lt))] = uint16_t(s);
-			if ((same & lt) == 0u) hist[key] = uint16_t(first + __popc(same));
+			const uint32_t same = __match_any_sync(0xffffffffu, key[k]);
+			uint32_t first = 0;
+			if (key[k] < bins) first = hist[key[k]];
+			__syncwarp();
+			if (key[k] < bins)
+			{
+				order[first + uint32_t(__popc(same & lt))] = uint16_t(s0 + uint32_t(k));
+				if ((same & lt) == 0u) hist[key[k]] = first + uint32_t(__popc(same));
+			}
+			__syncwarp();
 		}
-		__syncwarp();
 	}
 	__threadfence_block();
 	__syncwarp();
@@ -104,7 +133,7 @@ static __device__ __noinline__ void sortSamples(uint32_t pixel, uint32_t spp, ui
 // the trace kernel
 // ---------------------------------------------------------------------------------------------------------------
 template <bool SMEM, bool COUNT, int TRAV, bool SHARE, bool SPLIT = false>
-__global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderParams p)
+__global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_constant__ RenderParams p)
 {
 	extern __shared__ __align__(128) float4 smemScene[];
 	__shared__ uint64_t mbar;
@@ -127,8 +156,9 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 	__shared__ BeamEntry beamList[SHARE && TRAV >= 1 ? kTraceThreads / 32 : 1][kBeamMax];
 	int nBeam = -1;
 	// SPLIT: per-warp bin counters of sortSamples, and the warp's slice of the sample-order scratch
-	__shared__ uint16_t sortHist[SPLIT ? kTraceThreads / 32 : 1][SPLIT ? kSortBinsMax : 1];
-	const uint16_t *sampleOrder = nullptr;
+	__shared__ uint32_t sortHist[SPLIT ? kTraceThreads / 32 : 1][SPLIT ? kSortBinsMax : 1];
+	// (the warp's slice of the scratch is recomputed where it is used: two pointers kept live cost four registers)
+	auto warpScratch = [&]() -> char * { return sortScratchOfWarp(p); };
 
 	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t totalPixels = p.width * p.height;
@@ -167,7 +197,8 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 					{
 						sample = mine;
 						if constexpr (SPLIT)
-							if (sampleOrder != nullptr) sample = __ldcg(sampleOrder + mine); // the pixel's samples in the order of their first scattering direction
+							if (p.sortScratch != nullptr && !p.sortIgnore) // the pixel's samples in the order of their first scattering direction
+								sample = __ldcg(reinterpret_cast<const uint16_t *>(warpScratch()) + mine);
 						generate = true;
 					}
 					wNext = min(p.spp, wNext + uint32_t(__popc(needMask)));
@@ -206,9 +237,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const RenderPara
 					{
 						if (p.sortScratch != nullptr)
 						{
-							uint16_t *mine = p.sortScratch + (size_t(blockIdx.x) * (kTraceThreads / 32) + (threadIdx.x >> 5)) * 2u * p.sortStride;
-							sortSamples(pixel, p.spp, p.sampleOffset, p.sampleStride, p.seedLo, p.seedHi, p.sortBitsA, p.sortBitsB, mine, mine + p.sortStride, sortHist[threadIdx.x >> 5]);
-							sampleOrder = mine;
+							sortSamples(pixel, &p, sortHist[threadIdx.x >> 5]);
 						}
 					}
 					if constexpr (TRAV >= 1)

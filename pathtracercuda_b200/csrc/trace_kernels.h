@@ -34,9 +34,10 @@ struct RenderParams
 	uint32_t maxBounces;
 	uint32_t regenLow = 1; // one-pixel-per-warp kernel: idle lanes wait until this many can start new samples together
 	// one-pixel-per-warp kernel: the samples of a pixel are handed out in the order of their first scattering direction
-	// (sortSamples, trace_kernels.cu).  sortScratch = 2 x sortStride uint16 per warp of the grid; 0 = samples in index order
+	// (sortSamples, trace_kernels.cu).  sortScratch = sortStride x 4 bytes per warp of the grid; 0 = samples in index order
 	uint16_t *sortScratch = nullptr;
 	uint32_t sortStride = 0;
+	uint32_t sortIgnore = 0; // timing aid: sort, then hand the samples out in index order all the same
 	uint32_t sortBitsA = 4, sortBitsB = 2; // bins of the first / second random (2^(A+B) bins, 32..256)
 	uint32_t beam = 0;     // one-pixel-per-warp kernel: camera rays take their leaves from the pixel's beam list (trace_device.cuh)
 };
