@@ -6,9 +6,11 @@ config 3: 4096 spp) in Mrays/s, on N B200s of one node.
   (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
 
 A "step" = one complete render of the configuration: every pixel, `spp` samples, up to 5 path segments per sample
-(ray = one closest-hit query, sample = one path).  With N GPUs the samples of every pixel are partitioned
-across the ranks (global Philox sample indices, so the sample set is the same at any N) and the float4 accumulation
-buffers are summed with ONE NCCL reduce inside the timed region: strong scaling.
+(ray = one closest-hit query, sample = one path).  With N GPUs the work is partitioned
+across the ranks - by default the PIXELS (rank r renders pixels r, r+N, ... with all their samples: a pixel's samples stay
+on one GPU, which the per-pixel beam walk and sample order of long renders need; the image is bit-identical to the
+single-GPU one), with --partition samples the SAMPLES of every pixel (global Philox sample indices, so the sample set is
+the same at any N) - and the float4 accumulation buffers are summed with ONE NCCL reduce inside the timed region: strong scaling.
 
   value   rays of the whole job / device time of the step (CUDA events around the trace kernel on its own stream +
           CUDA events around the reduce), max over ranks; scene and accumulation buffer resident in HBM
@@ -184,13 +186,15 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--partition", default="pixels", choices=["pixels", "samples"],
+                    help="N > 1: what is split over the GPUs (pathtracercuda_b200/distributed.py); the single reduce is the same")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
     import pathtracercuda_b200 as pt
-    from pathtracercuda_b200.distributed import attach_torch_accumulator, partition_samples, reduce_accumulation
+    from pathtracercuda_b200.distributed import attach_torch_accumulator, configure_partition, reduce_accumulation
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -209,9 +213,7 @@ def main():
     cam = P.loadSceneFile(path, cwd=scene_cwd)
     P.setOption("variant", args.variant)
     accum = attach_torch_accumulator(P, torch.device("cuda", local))
-    off, stride, count = partition_samples(args.spp, rank, world)
-    P.setOption("sample_stride", stride)
-    P.setOption("sample_offset", off)
+    count = configure_partition(P, args.spp, rank, world, args.partition)  # spp argument of pt_render on this rank
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local}")
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
@@ -320,7 +322,9 @@ def main():
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_label(args.spp),
-                       "spp": args.spp, "spp_per_gpu": count, "parallelism": f"sample-partitioned x{world} + 1 NCCL reduce" if world > 1 else "single GPU",
+                       "spp": args.spp, "spp_per_gpu": count,
+                       "parallelism": ((f"pixel-partitioned x{world} (rank r: pixels r, r+{world}, ... with all {args.spp} samples; the other pixels of its buffer zero)" if args.partition == "pixels"
+                                        else f"sample-partitioned x{world} (rank r: samples r, r+{world}, ... of every pixel)") + " + 1 NCCL sum-reduce of the float4 accumulation buffers") if world > 1 else "single GPU",
                        "l2": f"flushed between steps (256 MiB memset); scene ({st0.scene_bytes / 1e3:.0f} KB) " + ("is staged in shared memory" if st0.scene_in_smem else "is read through L1/L2") + f", output {W * H * 16 / 1e6:.0f} MB accumulation buffer",
                        "kernel_variant": args.variant},
             "samples_per_s": W * H * args.spp / ms_step * 1e3, "samples_per_s_per_gpu": W * H * args.spp / ms_step * 1e3 / world, "rays_per_sample": rays_step / (W * H * args.spp),

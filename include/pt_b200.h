@@ -123,6 +123,9 @@ const float *pt_get_hdr_mean(pt_context *ctx);
  *  "seed"            Philox key (default 1984, cf. kernels/initRandState.cu:16)
  *  "sample_offset"   global index of the first sample of the next pt_render (multi-GPU sample partition)
  *  "sample_stride"   distance between this context's consecutive global sample indices (1 = contiguous)
+ *  "pixel_offset"    multi-GPU pixel partition: this context renders the pixels offset, offset + stride, ... (row-major index)
+ *  "pixel_stride"    with all of their samples; with stride > 1 a pt_render that restarts the accumulation zeroes the buffer first,
+ *                    so that the sum of the ranks' buffers is the image (default 0 / 1: every pixel)
  *  "frames_per_spp"  k>0: a pt_render of spp samples counts ceil(spp/k) frames for the Q1 normalisation
  *                    (k=8 reproduces the reference headless CLI, main.cpp:271-278); 0: one frame per call
  *  "count_work"      1: count node visits / primitive tests / shades / misses (slower)

@@ -59,6 +59,7 @@ struct pt_context
 	// options
 	uint64_t seed = 1984;
 	uint32_t sampleOffset = 0, sampleStride = 1, sampleCursor = 0;
+	uint32_t pixelOffset = 0, pixelStride = 1; // multi-GPU pixel partition: this context renders pixels offset, offset + stride, ...
 	uint32_t framesPerSpp = 0, maxBounces = 5, maxLeaf = 4;
 	LaunchConfig launch;
 	pt_stats stats;
@@ -305,6 +306,8 @@ int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ign
 	CK(cudaMemsetAsync(c->counters, 0, kCtrCount * sizeof(unsigned long long), c->stream));
 	CK(cudaEventRecord(c->evStart, c->stream));
 	const bool run = c->nodeCount >= 1 && c->primCount >= 1 && spp > 0; // Pathtracer.cpp:174
+	// pixel partition: the pixels of the other ranks hold zeros, so that the sum over ranks is the image
+	if (run && ignore_history && c->pixelStride > 1u) CK(cudaMemsetAsync(c->accum, 0, size_t(c->width) * c->height * sizeof(float4), c->stream));
 	if (run)
 	{
 		RenderParams p;
@@ -318,6 +321,8 @@ int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ign
 		p.ignoreHistory = ignore_history ? 1u : 0u;
 		p.sampleOffset = c->sampleCursor;
 		p.sampleStride = c->sampleStride;
+		p.pixelOffset = c->pixelOffset;
+		p.pixelStride = c->pixelStride;
 		p.seedLo = uint32_t(c->seed);
 		p.seedHi = uint32_t(c->seed >> 32);
 		p.maxBounces = c->maxBounces;
@@ -367,7 +372,11 @@ int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ign
 	{
 		unsigned long long h[kCtrCount];
 		CK(cudaMemcpy(h, c->counters, sizeof h, cudaMemcpyDeviceToHost));
-		c->stats.samples = (unsigned long long)c->width * c->height * spp;
+		{
+			const unsigned long long all = (unsigned long long)c->width * c->height;
+			const unsigned long long own = all > c->pixelOffset ? (all - c->pixelOffset + c->pixelStride - 1u) / c->pixelStride : 0ull;
+			c->stats.samples = own * spp;
+		}
 		memcpy(c->rawCounters, h, sizeof h);
 		if (h[kCtrError] != 0) return setError(PT_E_CUDA, "pt_render: wavefront scheduler watchdog fired (code " + std::to_string(h[kCtrError]) + ")");
 		c->stats.rays = h[kCtrRays];
@@ -439,6 +448,8 @@ int pt_set_option(pt_context *c, const char *key, double value)
 	if (k == "seed") c->seed = uint64_t(value);
 	else if (k == "sample_offset") { c->sampleOffset = uint32_t(value); c->sampleCursor = c->sampleOffset; }
 	else if (k == "sample_stride") c->sampleStride = value < 1 ? 1u : uint32_t(value);
+	else if (k == "pixel_offset") c->pixelOffset = value < 0 ? 0u : uint32_t(value);
+	else if (k == "pixel_stride") c->pixelStride = value < 1 ? 1u : uint32_t(value);
 	else if (k == "frames_per_spp") c->framesPerSpp = uint32_t(value);
 	else if (k == "count_work") c->launch.countWork = value != 0;
 	else if (k == "smem_scene") c->launch.smemScene = value != 0;

@@ -161,7 +161,9 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 	auto warpScratch = [&]() -> char * { return sortScratchOfWarp(p); };
 
 	const uint32_t lane = threadIdx.x & 31u;
-	const uint32_t totalPixels = p.width * p.height;
+	// the work counter hands out LOCAL indices: pixel = local * pixelStride + pixelOffset (all pixels for stride 1)
+	const uint32_t allPixels = p.width * p.height;
+	const uint32_t totalPixels = allPixels > p.pixelOffset ? (allPixels - p.pixelOffset + p.pixelStride - 1u) / p.pixelStride : 0u;
 	const float invW = 1.0f / float(p.width), invH = 1.0f / float(p.height);
 	const V3 camO = mk(p.cam.origin[0], p.cam.origin[1], p.cam.origin[2]);
 
@@ -231,7 +233,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 					if (lane == 0) next = atomicAdd(&p.counters[kCtrWork], 1ull);
 					next = __shfl_sync(0xffffffffu, next, 0);
 					if (next >= totalPixels) break;
-					pixel = uint32_t(next);
+					pixel = uint32_t(next) * p.pixelStride + p.pixelOffset;
 					wNext = 0;
 					if constexpr (SPLIT)
 					{
@@ -281,7 +283,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 			{
 				const unsigned long long mine = base + __popc(needMask & ((1u << lane) - 1u));
 				if (mine >= totalPixels) { active = false; pixel = kInvalid; }
-				else { pixel = uint32_t(mine); sample = 0; color = mk(0.0f, 0.0f, 0.0f); }
+				else { pixel = uint32_t(mine) * p.pixelStride + p.pixelOffset; sample = 0; color = mk(0.0f, 0.0f, 0.0f); }
 			}
 		}
 		if (!__any_sync(0xffffffffu, active)) break;

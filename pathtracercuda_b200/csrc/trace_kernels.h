@@ -30,6 +30,7 @@ struct RenderParams
 	unsigned long long *counters;
 	uint32_t width, height, spp, ignoreHistory;
 	uint32_t sampleOffset, sampleStride;
+	uint32_t pixelOffset = 0, pixelStride = 1; // this launch renders pixels offset, offset + stride, ... (multi-GPU pixel partition)
 	uint32_t seedLo, seedHi;
 	uint32_t maxBounces;
 	uint32_t regenLow = 1; // one-pixel-per-warp kernel: idle lanes wait until this many can start new samples together

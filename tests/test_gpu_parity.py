@@ -311,6 +311,30 @@ def test_sample_order_changes_nothing_but_the_order():
     assert np.allclose(run(1, sort_bits_a=5, sort_bits_b=2)[0], a, rtol=3e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("spp", [24, 320])
+def test_pixel_partition_sums_to_the_single_gpu_image(spp):
+    """multi-GPU pixel partition (options pixel_offset / pixel_stride): rank r renders pixels r, r+N, ... with all their
+    samples and leaves zeros elsewhere, so the sum of the ranks' buffers IS the single-GPU image, bit for bit - here the
+    three 'ranks' are three contexts on one GPU; also the accumulating second call"""
+    W, H, N = 150, 70, 3
+    def run(offset, stride):
+        with pt.Pathtracer(W, H) as P:
+            cam = P.loadSceneFile(f"{pt.ASSETS}/scenes/generated_scene.json", cwd=pt.ASSETS)
+            P.setOption("pixel_stride", stride)
+            P.setOption("pixel_offset", offset)
+            P.render(cam, spp, True)
+            P.render(cam, spp, False)
+            return P.getHDRMean().copy(), P.stats()
+    full, st = run(0, 1)
+    parts = [run(r, N) for r in range(N)]
+    total = sum(p[0][..., :3] for p in parts)
+    assert np.array_equal(bits(total), bits(full[..., :3]))
+    assert sum(p[1].samples for p in parts) == st.samples == W * H * spp and sum(p[1].rays for p in parts) == st.rays
+    for r, (img, _) in enumerate(parts):
+        own = (np.arange(W * H) % N == r).reshape(H, W)
+        assert not img[..., :3][~own].any() and img[..., :3][own].any()
+
+
 def test_texture_unit_matches_software_filter():
     """texture taps through the texture unit (one TEX instruction, 1.8 fixed-point filter weights - the reference's own
     path) against the fp32 software filter over the packed texels (option tex_unit=0): same image up to the weights'

@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 import pathtracercuda_b200 as pt
-from pathtracercuda_b200.distributed import partition_samples, reduce_accumulation
+from pathtracercuda_b200.distributed import configure_partition, partition_pixels, partition_samples, reduce_accumulation
 
 
 def test_partition_covers_every_sample_once():
@@ -25,6 +25,26 @@ def test_partition_covers_every_sample_once():
         partition_samples(8, 2, 2)
 
 
+def test_pixel_partition_covers_every_pixel_once_and_sets_the_options():
+    for world in (1, 2, 3, 8):
+        owner = np.full(1000, -1)
+        for r in range(world):
+            off, stride = partition_pixels(r, world)
+            assert (owner[off::stride] == -1).all()
+            owner[off::stride] = r
+        assert (owner >= 0).all() and np.bincount(owner).max() - np.bincount(owner).min() <= 1
+    class Stub:
+        def __init__(self): self.opts = {}
+        def setOption(self, k, v): self.opts[k] = v
+    t = Stub()
+    assert configure_partition(t, 4096, 3, 8, "pixels") == 4096
+    assert t.opts == {"sample_stride": 1, "sample_offset": 0, "pixel_stride": 8, "pixel_offset": 3}
+    assert configure_partition(t, 4096, 3, 8, "samples") == 512
+    assert t.opts == {"sample_stride": 8, "sample_offset": 3, "pixel_stride": 1, "pixel_offset": 0}
+    with pytest.raises(ValueError):
+        configure_partition(t, 8, 0, 2, "tiles")
+
+
 def _worker(rank, world, port, out_dir):
     from oracle import orc
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -37,9 +57,16 @@ def _worker(rank, world, port, out_dir):
     acc, rays = O.render(cam, W, H, count, sample_offset=off, sample_stride=stride)
     t = torch.from_numpy(acc)
     reduce_accumulation(t, dst=0)
+    # pixel partition: all samples of this rank's pixels (the oracle renders the frame, the rank keeps what it owns - the
+    # CUDA kernel only ever touches its own pixels), zeros elsewhere, the same reduce
+    full, _ = O.render(cam, W, H, spp)
+    poff, pstride = partition_pixels(rank, world)
+    own = (np.arange(W * H) % pstride == poff).reshape(H, W)
+    t2 = torch.from_numpy(np.where(own[..., None], full, np.float32(0)).astype(np.float32))
+    reduce_accumulation(t2, dst=0)
     if rank == 0:
-        full, _ = O.render(cam, W, H, spp)
         np.save(os.path.join(out_dir, "reduced.npy"), t.numpy())
+        np.save(os.path.join(out_dir, "reduced_pixels.npy"), t2.numpy())
         np.save(os.path.join(out_dir, "full.npy"), full)
     dist.barrier()
     dist.destroy_process_group()
@@ -55,3 +82,5 @@ def test_two_rank_reduce_equals_single_render(tmp_path):
     # same sample set, different float summation order (per-rank partial sums, then the reduce)
     assert np.allclose(red[..., :3], full[..., :3], rtol=1e-5, atol=1e-5)
     assert np.all(red[..., 3] == 2.0)  # every rank wrote alpha = 1 (trace.cu:198); the reduce sums them
+    # pixel partition: x + 0 = x, the reduced image is the single-process image bit for bit (alpha 1: one owner per pixel)
+    assert np.array_equal(np.load(tmp_path / "reduced_pixels.npy").view(np.uint32), full.view(np.uint32))
