@@ -57,6 +57,8 @@ def resolve_scene(args):
 
 def workload_label(spp):
     cfg = {"generated_scene": "BASELINE.json config 3", "cornell_box": "BASELINE.json config 2"}.get(SCENE, "BASELINE.json config 4")
+    if SCENE == "generated_scene" and (W, H) == (3840, 2160):
+        cfg = "BASELINE.json config 5"
     return f"{SCENE}.json {W}x{H} {spp} spp ({cfg}), stand-in earth.png/skybox.hdr (reference assets not in its checkout)"
 
 # algorithmic FP32 operations per unit of work, counted from the reference source
