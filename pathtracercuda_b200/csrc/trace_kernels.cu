@@ -4,11 +4,14 @@
 // kernels/initRandState.cu, kernels/tonemap.cu) and the device halves of Hittable.inl / Material.inl / MonteCarlo.h /
 // brdf.h / Camera.inl.  Same estimator, different machine mapping:
 //
-//   * persistent CTAs (one wave sized to the SM count); every lane owns a pixel and regenerates a new path the moment
-//     its current one terminates, so warps stay full through all five path segments instead of idling until the
-//     longest path of the warp ends (the reference runs one thread per pixel with no compaction);
-//   * pixels are handed out by a warp-aggregated atomic (ballot + popc prefix) - no per-pixel RNG state, no 48 B/pixel
-//     buffer: Philox4x32-10 keyed on (seed), counter (pixel, sample, bounce slot);
+//   * persistent CTAs (one wave sized to the SM count) with path regeneration, so warps stay full through all five path
+//     segments instead of idling until the longest path of the warp ends (the reference runs one thread per pixel with no
+//     compaction).  Long renders (SHARE + SPLIT, from 64 spp): ONE PIXEL PER WARP - the lanes trace samples of the same
+//     pixel; the leaves its camera rays can reach are found once per pixel (pixel beams, trace_device.cuh beamLeaves); a
+//     pass of the main loop is either for camera rays or for scattered rays; from 1024 spp the samples are handed out in
+//     the order of their first scattering direction (sortSamples below).  Short renders: one pixel per lane, pixels handed
+//     out by a warp-aggregated atomic (ballot + popc prefix);
+//   * no per-pixel RNG state, no 48 B/pixel buffer: Philox4x32-10 keyed on (seed), counter (pixel, sample, bounce slot);
 //   * the BVH is 64-byte two-box nodes + 64-byte primitives read with 128-bit loads; when nodes+primitives fit in
 //     shared memory they are staged there once per CTA with a TMA bulk copy (cp.async.bulk + mbarrier);
 //   * ray/box tests use a precomputed reciprocal direction (12 FMA per node instead of the reference's 3 IEEE
