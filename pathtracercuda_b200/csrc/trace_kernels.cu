@@ -159,6 +159,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 	__shared__ BeamEntry beamList[SHARE && TRAV >= 1 ? kTraceThreads / 32 : 1][kBeamMax];
 	int nBeam = -1;
 	// SPLIT: per-warp bin counters of sortSamples, and the warp's slice of the sample-order scratch
+	__shared__ float2 pixelXY[SHARE ? kTraceThreads / 32 : 1]; // SHARE: (x, y) of the warp's pixel, once per pixel instead of once per sample
 	__shared__ uint32_t sortHist[SPLIT ? kTraceThreads / 32 : 1][SPLIT ? kSortBinsMax : 1];
 	// (the warp's slice of the scratch is recomputed where it is used: two pointers kept live cost four registers)
 	auto warpScratch = [&]() -> char * { return sortScratchOfWarp(p); };
@@ -238,6 +239,12 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 					if (next >= totalPixels) break;
 					pixel = uint32_t(next) * p.pixelStride + p.pixelOffset;
 					wNext = 0;
+					{
+						uint32_t px, py;
+						pixelToXY(pixel, p.width, p.height, px, py);
+						if (lane == 0) pixelXY[threadIdx.x >> 5] = make_float2(float(px), float(py));
+						__syncwarp();
+					}
 					if constexpr (SPLIT)
 					{
 						if (p.sortScratch != nullptr)
@@ -318,10 +325,16 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 			{
 				sampleIdx = p.sampleOffset + sample * p.sampleStride;
 				const uint4 r = philoxNI(pixel, sampleIdx, 0u, p.seedLo, p.seedHi);
-				uint32_t px, py;
-				pixelToXY(pixel, p.width, p.height, px, py);
-				const float u = (float(px) + uniform01(r.x)) * invW; // trace.cu:190
-				const float v = (float(py) + uniform01(r.y)) * invH;
+				float pxf, pyf;
+				if constexpr (SHARE) { const float2 xy = pixelXY[threadIdx.x >> 5]; pxf = xy.x; pyf = xy.y; }
+				else
+				{
+					uint32_t px, py;
+					pixelToXY(pixel, p.width, p.height, px, py);
+					pxf = float(px); pyf = float(py);
+				}
+				const float u = (pxf + uniform01(r.x)) * invW; // trace.cu:190
+				const float v = (pyf + uniform01(r.y)) * invH;
 				rz = r.z; rw = r.w;
 				ro = camO;
 				rd = cameraDir<kHotExact>(p.cam, u, v);
