@@ -63,7 +63,7 @@ typedef struct pt_camera_desc {
 	float aspect;
 } pt_camera_desc;
 
-/* counters of the last pt_render call (the wavefront queues make these free; SURVEY.md §5 "Tracing"). */
+/* counters of the last pt_render call (SURVEY.md §5 "Tracing"). */
 typedef struct pt_stats {
 	uint64_t samples;      /* paths started (= W*H*spp) */
 	uint64_t rays;         /* closest-hit queries (camera + scattered segments, <=5 per sample) */
@@ -118,6 +118,8 @@ const uint8_t *pt_get_ldr(pt_context *ctx);
 
 /* W*H*4 floats of the TRUE per-sample mean (accumulation / total samples), library-owned. */
 const float *pt_get_hdr_mean(pt_context *ctx);
+/* W*H*4 floats of the raw accumulation buffer (per-pixel sums, alpha = 1; what kernels/tonemap.cu reads), library-owned. */
+const float *pt_get_hdr_sum(pt_context *ctx);
 
 /* Options (all doubles):
  *  "seed"            Philox key (default 1984, cf. kernels/initRandState.cu:16)
@@ -126,6 +128,8 @@ const float *pt_get_hdr_mean(pt_context *ctx);
  *  "pixel_offset"    multi-GPU pixel partition: this context renders the pixels offset, offset + stride, ... (row-major index)
  *  "pixel_stride"    with all of their samples; with stride > 1 a pt_render that restarts the accumulation zeroes the buffer first,
  *                    so that the sum of the ranks' buffers is the image (default 0 / 1: every pixel)
+ *  "total_samples" / "accumulated_frames"  overwrite the counts the image getters normalise by (after a multi-GPU reduce the
+ *                    destination's buffer holds the samples of all ranks)
  *  "frames_per_spp"  k>0: a pt_render of spp samples counts ceil(spp/k) frames for the Q1 normalisation
  *                    (k=8 reproduces the reference headless CLI, main.cpp:271-278); 0: one frame per call
  *  "count_work"      1: count node visits / primitive tests / shades / misses (slower)
@@ -136,8 +140,17 @@ const float *pt_get_hdr_mean(pt_context *ctx);
  *  "variant"         trace kernel variant, 0 = default (see csrc/trace_kernels.h LaunchConfig)
  *  "beam"            pixel beams for camera rays (one-pixel-per-warp kernels): 1 on, 0 off, -1 auto (default: on from 128 spp)
  *  "regen_low"       one-pixel-per-warp kernels: idle lanes wait until this many can start new samples together (0 = default)
- *  "sort_samples"    one-pixel-per-warp kernels: hand a pixel's samples out in the order of their first scattering direction
- *                    (an order only: same Philox counters, same paths): 1 on, 0 off, -1 auto (default: on from 1024 spp)
+ *  "stratify"        one-pixel-per-warp kernels: stratify the two randoms of the FIRST scattering direction over the samples of a
+ *                    pixel (2^k cells of equal sample count, k <= 7; the cell is the top bits, the Philox draw the rest).  Same
+ *                    expectation as the reference's plain draws (Material.inl:40-41), never more variance, and the lanes of a
+ *                    warp scatter into the same cell (coherent traversal): 1 on, 0 off, -1 auto (default: on from 128 spp)
+ *  "sort_samples"    alternative to "stratify" (used when that is off): hand a pixel's samples out in the order of their first
+ *                    scattering direction (an order only: same Philox counters, same paths): 1 on, 0 off (default)
+ *  "smem_stack"      traversal stack in shared memory instead of local memory: 1 / -1 (default) when it fits, 0 off
+ *  "jitter"          0: every sample goes through the pixel centre, u = (x + 0.5) / W (parity aid; default 1 = trace.cu:190-191)
+ *  "first_hit"       1: pt_render also records, per pixel, the scene index and t of the closest hit of the camera ray AS FOUND BY
+ *                    THE RENDER KERNEL ITSELF (pt_get_first_hit); with "jitter" = 0 this is the primary-pass gate on the
+ *                    production traversal (beams, MUFU reciprocals and all)
  *  "tex_unit"        1 (default): texture taps through CUDA texture objects, as the reference (Pathtracer.cpp:259-288);
  *                    0: fp32 bilinear filter in software over the packed texels */
 int pt_set_option(pt_context *ctx, const char *key, double value);
@@ -153,6 +166,10 @@ void pt_camera_translate(pt_camera_desc *camera, float x, float y, float z);
 /* Deterministic primary-ray pass (parity gate): pixel-centre rays u=(x+0.5)/W, v=(y+0.5)/H, t_min=0.001; writes the
  * scene-order object index (or -1) and hit t (0 on miss) per pixel into HOST buffers of W*H elements. */
 int pt_primary_pass(pt_context *ctx, const pt_camera_desc *camera, int32_t *hit_index, float *hit_t);
+
+/* After a pt_render with option "first_hit" = 1: scene-order object index (-1: miss) and t (0 on a miss) of the camera ray's
+ * closest hit per pixel, as found by the render kernel, into HOST buffers of W*H elements. */
+int pt_get_first_hit(pt_context *ctx, int32_t *hit_index, float *hit_t);
 
 /* Closest-hit queries for caller-supplied rays (n rays, origin/direction as xyz triples in host memory). */
 int pt_trace_rays(pt_context *ctx, size_t n, const float *origins, const float *directions, float t_min,

@@ -120,7 +120,10 @@ class Oracle:
         self.L.orc_trace_rays(self.s, n, _p(o), _p(d), tmin, _p(idx), _p(t), _p(nrm))
         return idx, t, nrm
 
-    def render(self, cam, w, h, spp, seed=1984, sample_offset=0, sample_stride=1, accum=None, max_bounces=5):
+    def render(self, cam, w, h, spp, seed=1984, sample_offset=0, sample_stride=1, accum=None, max_bounces=5, stratify=None):
+        """stratify: the product's first-bounce stratification (include/pt_b200.h option "stratify"); None = the product's
+        default, on from 128 spp"""
+        self.L.orc_set_stratify(int(spp >= 128 if stratify is None else stratify))
         add = accum is not None
         if accum is None:
             accum = np.zeros((h, w, 4), np.float32)

@@ -761,6 +761,22 @@ void orc_trace_rays(const orc_scene *s, size_t n, const float *o, const float *d
 		if (nrm) { nrm[3 * i] = hit ? rec.n.x : 0.0f; nrm[3 * i + 1] = hit ? rec.n.y : 0.0f; nrm[3 * i + 2] = hit ? rec.n.z : 0.0f; }
 	}
 }
+/* First-bounce stratification — NOT in the reference; the product's one-pixel-per-warp kernels apply it by default from
+ * 128 spp (include/pt_b200.h option "stratify", csrc/trace_kernels.h RenderParams::strataPer) and the path-for-path tests
+ * need the checker to draw the same numbers.  The launch's first per << k samples of a pixel (local index i) take the two
+ * randoms of the first scattering direction from cell i / per of a 2^bitsA x 2^bitsB grid: the cell gives the top bits, the
+ * Philox draw the bits below.  Integer arithmetic only, so CPU and GPU agree to the bit.  Same rule as pt_render. */
+static int g_stratify = 0;
+void orc_set_stratify(int on) { g_stratify = on; }
+static void strataFor(uint32_t spp, uint32_t *per, uint32_t *bitsA, uint32_t *bitsB)
+{
+	*per = 0; *bitsA = *bitsB = 0;
+	if (!g_stratify || spp < 4u || spp >= (1u << 21)) return;
+	uint32_t k = 2;
+	while (k < 7u && (spp >> (k + 1u)) >= 32u) ++k;
+	while (k > 2u && (spp >> k) == 0u) --k;
+	*bitsA = (k + 1u) / 2u; *bitsB = k / 2u; *per = spp >> k;
+}
 /* traceKernel  kernels/trace.cu:158-199 with the Philox stream of north_star item 4 */
 uint64_t orc_render(const orc_scene *s, const pt_camera_desc *cam, uint32_t w, uint32_t h, uint32_t spp, uint64_t seed,
                     uint32_t sample_offset, uint32_t sample_stride, int add, int max_bounces, float *accum)
@@ -768,6 +784,8 @@ uint64_t orc_render(const orc_scene *s, const pt_camera_desc *cam, uint32_t w, u
 	cam_t k = makeCamera(cam);
 	uint64_t rays = 0;
 	const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+	uint32_t per, bitsA, bitsB;
+	strataFor(spp, &per, &bitsA, &bitsB);
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : rays)
 	for (int y = 0; y < (int)h; ++y)
 		for (uint32_t x = 0; x < w; ++x)
@@ -778,6 +796,13 @@ uint64_t orc_render(const orc_scene *s, const pt_camera_desc *cam, uint32_t w, u
 			{
 				uint32_t sample = sample_offset + i * sample_stride, rng[4];
 				orc_philox(pixel, sample, 0, 0, k0, k1, rng);
+				if (per && i < (per << (bitsA + bitsB)))
+				{
+					const uint32_t cell = i / per, a = cell >> bitsB, bMask = (1u << bitsB) - 1u;
+					const uint32_t b = (a & 1u) ? bMask - (cell & bMask) : (cell & bMask);
+					rng[2] = (a << (32u - bitsA)) | (rng[2] >> bitsA);
+					rng[3] = (b << (32u - bitsB)) | (rng[3] >> bitsB);
+				}
 				float u = (x + orc_uniform(rng[0])) / (float)w;
 				float v = (y + orc_uniform(rng[1])) / (float)h;
 				ray_t r = cameraRay(&k, u, v);

@@ -3,6 +3,8 @@
 // unmodified reference binary (ref_pt) cannot do:
 //   primary : deterministic primary-ray pass — pixel-centre rays through the reference's hitBVH
 //             (kernels/trace.cu:28-98), dumping scene-order hit index and t per pixel (the parity gate).
+//   tonemap : the reference's tonemap kernel (kernels/tonemap.cu, linked from its own object file) over an accumulation
+//             buffer read from a file: the byte-exact gate for our tonemapKernel.
 //   count   : the reference traceKernel's loop (kernels/trace.cu:158-199, getColor :101-156) with one counter
 //             added, to learn how many rays (hitBVH calls) the reference traces for a given scene/size/spp
 //             with its own XORWOW seeds (kernels/initRandState.cu:16) in its own 8-spp slices (main.cpp:271-278).
@@ -16,7 +18,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <unordered_map>
 #include "pathtracer/kernels/trace.cu"
+#include "pathtracer/kernels/tonemap.h"
 #include "../../include/pt_b200.h"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_) { fprintf(stderr, "CUDA error %d (%s) at %s:%d\n", (int)e_, cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
@@ -100,6 +104,30 @@ int main(int argc, char **argv)
 		fprintf(stderr, "usage: ref_gpu primary <scene.blob> <out.bin> | ref_gpu count <scene.blob> <spp>\n");
 		return 2;
 	}
+	if (strcmp(argv[1], "tonemap") == 0)
+	{
+		// ref_gpu tonemap <accum.bin> <out.bin> <width> <height> <accumulatedSampleCount>: the reference's own tonemap kernel
+		// (kernels/tonemap.cu:4-27, launched as in Pathtracer.cpp:322-328) over a float4 accumulation buffer from a file
+		if (argc < 7) { fprintf(stderr, "usage: ref_gpu tonemap <accum.bin> <out.bin> <width> <height> <count>\n"); return 2; }
+		const uint32_t W = (uint32_t)atoi(argv[4]), H = (uint32_t)atoi(argv[5]), count = (uint32_t)atoi(argv[6]);
+		std::vector<float> acc(size_t(W) * H * 4);
+		FILE *fi = fopen(argv[2], "rb");
+		if (!fi || fread(acc.data(), 16, size_t(W) * H, fi) != size_t(W) * H) { fprintf(stderr, "cannot read %s\n", argv[2]); return 2; }
+		fclose(fi);
+		float4 *dAcc; uchar4 *dOut;
+		CK(cudaMalloc(&dAcc, acc.size() * 4)); CK(cudaMalloc(&dOut, size_t(W) * H * 4));
+		CK(cudaMemcpy(dAcc, acc.data(), acc.size() * 4, cudaMemcpyHostToDevice));
+		dim3 threads(8, 8, 1), blocks((W + 7) / 8, (H + 7) / 8, 1);
+		tonemap<<<blocks, threads>>>(dOut, dAcc, W, H, count);
+		CK(cudaGetLastError()); CK(cudaDeviceSynchronize());
+		std::vector<unsigned char> out(size_t(W) * H * 4);
+		CK(cudaMemcpy(out.data(), dOut, out.size(), cudaMemcpyDeviceToHost));
+		FILE *fo = fopen(argv[3], "wb");
+		if (!fo) { fprintf(stderr, "cannot write %s\n", argv[3]); return 2; }
+		fwrite(out.data(), 1, out.size(), fo); fclose(fo);
+		printf("{\"mode\":\"tonemap\",\"width\":%u,\"height\":%u,\"count\":%u}\n", W, H, count);
+		return 0;
+	}
 	FILE *f = fopen(argv[2], "rb");
 	if (!f) { fprintf(stderr, "cannot open %s\n", argv[2]); return 2; }
 	uint32_t hdr[4];
@@ -123,11 +151,20 @@ int main(int argc, char **argv)
 	std::vector<int32_t> bvhToScene(N, -1);
 	std::vector<char> used(N, 0);
 	const auto &elems = bvh.getElements();
+	// BVH order -> scene order: BVH::build reorders copies of the CpuHittables; match them back by their bytes (hashed: the
+	// synthetic scenes of BASELINE config 4 have up to a million objects), duplicates in scene order
+	std::unordered_multimap<uint64_t, uint32_t> byHash;
+	byHash.reserve(N * 2);
+	auto hashOf = [](const CpuHittable &h) { uint64_t x = 1469598103934665603ull; const unsigned char *p = (const unsigned char *)&h; for (size_t k = 0; k < sizeof(CpuHittable); ++k) x = (x ^ p[k]) * 1099511628211ull; return x; };
+	for (size_t j = N; j-- > 0;) byHash.emplace(hashOf(objects[j]), (uint32_t)j);
 	for (size_t i = 0; i < elems.size(); ++i)
 	{
 		gpuH.push_back(elems[i].getGpuHittable());
-		for (size_t j = 0; j < N; ++j)
-			if (!used[j] && memcmp(&elems[i], &objects[j], sizeof(CpuHittable)) == 0) { used[j] = 1; bvhToScene[i] = (int32_t)j; break; }
+		auto range = byHash.equal_range(hashOf(elems[i]));
+		uint32_t bestJ = 0xffffffffu;
+		for (auto it = range.first; it != range.second; ++it)
+			if (!used[it->second] && it->second < bestJ && memcmp(&elems[i], &objects[it->second], sizeof(CpuHittable)) == 0) bestJ = it->second;
+		if (bestJ != 0xffffffffu) { used[bestJ] = 1; bvhToScene[i] = (int32_t)bestJ; }
 	}
 	Camera camera(vec3(cd.position[0], cd.position[1], cd.position[2]), vec3(cd.look_at[0], cd.look_at[1], cd.look_at[2]), vec3(cd.up[0], cd.up[1], cd.up[2]), cd.fovy, cd.aspect);
 

@@ -35,6 +35,7 @@ def load_library():
         "pt_get_timing_ms": (f32, [vp]),
         "pt_get_hdr": (vp, [vp]),
         "pt_get_hdr_mean": (vp, [vp]),
+        "pt_get_hdr_sum": (vp, [vp]),
         "pt_get_ldr": (vp, [vp]),
         "pt_set_option": (i32, [vp, cp, C.c_double]),
         "pt_get_stats": (i32, [vp, vp]),
@@ -42,6 +43,7 @@ def load_library():
         "pt_camera_translate": (None, [vp, f32, f32, f32]),
         "pt_primary_pass": (i32, [vp, vp, vp, vp]),
         "pt_trace_rays": (i32, [vp, sz, vp, vp, f32, vp, vp, vp]),
+        "pt_get_first_hit": (i32, [vp, vp, vp]),
         "pt_accum_device_ptr": (vp, [vp]),
         "pt_set_accum_device_ptr": (i32, [vp, vp]),
         "pt_load_scene_file": (i32, [vp, cp, vp]),
@@ -62,8 +64,8 @@ def load_library():
 
 
 EXPORTS = ["pt_create", "pt_destroy", "pt_set_scene", "pt_load_texture", "pt_load_texture_mem", "pt_set_skybox", "pt_render",
-           "pt_get_timing_ms", "pt_get_hdr", "pt_get_hdr_mean", "pt_get_ldr", "pt_set_option", "pt_get_stats", "pt_camera_rotate", "pt_camera_translate", "pt_primary_pass",
-           "pt_trace_rays", "pt_accum_device_ptr", "pt_set_accum_device_ptr", "pt_load_scene_file", "pt_parse_scene_file",
+           "pt_get_timing_ms", "pt_get_hdr", "pt_get_hdr_mean", "pt_get_hdr_sum", "pt_get_ldr", "pt_set_option", "pt_get_stats", "pt_camera_rotate", "pt_camera_translate", "pt_primary_pass",
+           "pt_trace_rays", "pt_get_first_hit", "pt_accum_device_ptr", "pt_set_accum_device_ptr", "pt_load_scene_file", "pt_parse_scene_file",
            "pt_write_png", "pt_write_hdr", "pt_read_image", "pt_free", "pt_last_error", "pt_version"]
 
 
@@ -208,6 +210,11 @@ class Pathtracer:
         a = self._img(self.L.pt_get_hdr_mean(self.h), np.float32)
         return a.copy() if copy else a
 
+    def getHDRSum(self, copy=True):
+        """the raw accumulation buffer (per-pixel sums, alpha = 1)"""
+        a = self._img(self.L.pt_get_hdr_sum(self.h), np.float32)
+        return a.copy() if copy else a
+
     def setOption(self, key, value):
         _check(self.L, self.L.pt_set_option(self.h, key.encode(), float(value)), "pt_set_option")
 
@@ -220,6 +227,13 @@ class Pathtracer:
         idx = np.zeros(self.width * self.height, np.int32)
         t = np.zeros(self.width * self.height, np.float32)
         _check(self.L, self.L.pt_primary_pass(self.h, C.byref(camera), _p(idx), _p(t)), "pt_primary_pass")
+        return idx, t
+
+    def firstHit(self):
+        """(index, t) per pixel of the camera rays' closest hits as found by the last render (option first_hit = 1)"""
+        idx = np.zeros(self.width * self.height, np.int32)
+        t = np.zeros(self.width * self.height, np.float32)
+        _check(self.L, self.L.pt_get_first_hit(self.h, _p(idx), _p(t)), "pt_get_first_hit")
         return idx, t
 
     def traceRays(self, origins, directions, t_min=0.001, normals=True):

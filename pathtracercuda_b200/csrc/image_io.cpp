@@ -61,6 +61,11 @@ bool decodePng(const uint8_t *d, size_t n, Image &out, std::string &err)
 	if (interlace) { err = "interlaced PNG not supported"; return false; }
 	int channels = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
 	if (!channels || !(depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)) { err = "unsupported PNG format"; return false; }
+	// the colour-type / bit-depth pairs the PNG specification allows: sub-byte depths only for greyscale and palette images,
+	// 16 bits not for palettes
+	if ((depth < 8 && !(ctype == 0 || ctype == 3)) || (depth == 16 && ctype == 3)) { err = "invalid PNG colour type / bit depth combination"; return false; }
+	// a corrupt or hostile IHDR must not turn into a giant allocation (stb_image's own limit is 2^24 per side)
+	if (w > (1u << 24) || h > (1u << 24) || uint64_t(w) * h > (1ull << 28)) { err = "PNG dimensions too large"; return false; }
 	if (ctype == 3 && palette.empty()) { err = "paletted PNG without PLTE"; return false; }
 	const size_t bpp = std::max<size_t>(1, size_t(channels) * depth / 8);
 	const size_t stride = (size_t(w) * channels * depth + 7) / 8;
@@ -225,7 +230,21 @@ bool readImage(const char *path, Image &out, std::string &err)
 	std::vector<uint8_t> data;
 	if (!readFile(path, data)) { err = std::string("cannot read ") + path; return false; }
 	const bool hdr = (data.size() >= 11 && !memcmp(data.data(), "#?RADIANCE\n", 11)) || (data.size() >= 7 && !memcmp(data.data(), "#?RGBE\n", 7));
-	return hdr ? decodeHdr(data.data(), data.size(), out, err) : decodePng(data.data(), data.size(), out, err);
+	if (hdr) return decodeHdr(data.data(), data.size(), out, err);
+	static const uint8_t pngSig[8] = { 137, 80, 78, 71, 13, 10, 26, 10 };
+	if (data.size() < 8 || memcmp(data.data(), pngSig, 8) != 0)
+	{
+		// the reference decodes textures with stb_image (also JPEG, BMP, TGA, PSD, GIF, PIC, PNM); here: PNG and Radiance HDR.
+		// Say so instead of silently rendering untextured.
+		const char *what = data.size() >= 3 && data[0] == 0xff && data[1] == 0xd8 ? "JPEG" : data.size() >= 2 && data[0] == 'B' && data[1] == 'M' ? "BMP"
+		                   : data.size() >= 4 && !memcmp(data.data(), "GIF8", 4) ? "GIF" : data.size() >= 4 && !memcmp(data.data(), "8BPS", 4) ? "PSD" : "unknown";
+		err = std::string("unsupported image format (") + what + "; supported: PNG, Radiance HDR): " + path;
+		fprintf(stderr, "pt_b200: %s\n", err.c_str());
+		return false;
+	}
+	const bool ok = decodePng(data.data(), data.size(), out, err);
+	if (!ok && err == "interlaced PNG not supported") fprintf(stderr, "pt_b200: %s: %s\n", err.c_str(), path);
+	return ok;
 }
 
 // ---- writers ------------------------------------------------------------------------------------------------

@@ -40,6 +40,9 @@ struct pt_context
 	unsigned long long *counters = nullptr;
 	void *sortScratch = nullptr; // per-warp sample order (RenderParams::sortScratch)
 	size_t sortScratchBytes = 0;
+	int32_t *firstHitIndex = nullptr; // option "first_hit": the render kernel's own first-hit (index, t) per pixel (parity aid)
+	float *firstHitT = nullptr;
+	bool firstHit = false, noJitter = false;
 	// scene
 	float4 *sceneBlob = nullptr;
 	Mat *mats = nullptr;
@@ -78,6 +81,26 @@ struct pt_context
 		}                                                                                                             \
 	} while (0)
 
+namespace
+{
+// device allocation freed on every return path
+struct DevBuf
+{
+	void *p = nullptr;
+	~DevBuf() { if (p) cudaFree(p); }
+	cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes); }
+	template <typename T> T *as() const { return static_cast<T *>(p); }
+};
+} // namespace
+
+// No C++ exception may cross the C boundary (std::bad_alloc from a huge scene or image would otherwise terminate the host)
+#define PT_TRY try {
+#define PT_CATCH(ret)                                                                                                 \
+	}                                                                                                                 \
+	catch (const std::bad_alloc &) { setError(PT_E_LIMIT, std::string(__func__) + ": out of memory"); return ret; }    \
+	catch (const std::exception &e) { setError(PT_E_LIMIT, std::string(__func__) + ": " + e.what()); return ret; }     \
+	catch (...) { setError(PT_E_LIMIT, std::string(__func__) + ": unknown exception"); return ret; }
+
 extern "C"
 {
 
@@ -87,6 +110,7 @@ void pt_free(void *p) { free(p); }
 
 int pt_create(uint32_t width, uint32_t height, int device, pt_context **out)
 {
+	PT_TRY
 	if (!out || width == 0 || height == 0) return setError(PT_E_INVALID, "pt_create: bad arguments");
 	*out = nullptr;
 	int count = 0;
@@ -125,6 +149,7 @@ int pt_create(uint32_t width, uint32_t height, int device, pt_context **out)
 #undef CKC
 	*out = c;
 	return PT_OK;
+	PT_CATCH(PT_E_LIMIT)
 }
 
 void pt_destroy(pt_context *c)
@@ -139,6 +164,8 @@ void pt_destroy(pt_context *c)
 	if (c->hostLdr) cudaFreeHost(c->hostLdr);
 	if (c->counters) cudaFree(c->counters);
 	if (c->sortScratch) cudaFree(c->sortScratch);
+	if (c->firstHitIndex) cudaFree(c->firstHitIndex);
+	if (c->firstHitT) cudaFree(c->firstHitT);
 	if (c->texDev) cudaFree(c->texDev);
 	if (c->sceneBlob) cudaFree(c->sceneBlob);
 	if (c->mats) cudaFree(c->mats);
@@ -153,6 +180,7 @@ void pt_destroy(pt_context *c)
 
 int pt_set_scene(pt_context *c, size_t count, const pt_object_desc *objects)
 {
+	PT_TRY
 	if (!c) return setError(PT_E_INVALID, "pt_set_scene: null context");
 	if (count == 0)
 	{
@@ -183,6 +211,7 @@ int pt_set_scene(pt_context *c, size_t count, const pt_object_desc *objects)
 	c->stats.bvh_depth = c->bvhDepth;
 	c->stats.scene_bytes = uint32_t(nodeBytes + primBytes + cs.mats.size() * sizeof(Mat));
 	return PT_OK;
+	PT_CATCH(PT_E_LIMIT)
 }
 
 // device copy of the texture table; with tex_unit = 0 the texture objects are left out and the kernels filter in software
@@ -199,6 +228,7 @@ static int uploadTextureTable(pt_context *c)
 
 uint32_t pt_load_texture_mem(pt_context *c, uint32_t width, uint32_t height, int is_hdr, const void *rgba)
 {
+	PT_TRY
 	if (!c || !rgba || width == 0 || height == 0) return 0;
 	if (c->textureCount >= kMaxTextures) return 0; // Pathtracer.cpp:236-240
 	if (cudaSetDevice(c->device) != cudaSuccess) return 0;
@@ -257,16 +287,19 @@ uint32_t pt_load_texture_mem(pt_context *c, uint32_t width, uint32_t height, int
 	++c->textureCount;
 	if (uploadTextureTable(c) != PT_OK) { --c->textureCount; return 0; }
 	return c->textureCount;
+	PT_CATCH(0u)
 }
 
 uint32_t pt_load_texture(pt_context *c, const char *path)
 {
+	PT_TRY
 	if (!c || !path) return 0;
 	if (c->textureCount >= kMaxTextures) return 0;
 	Image img;
 	std::string err;
 	if (!readImage(path, img, err)) { g_lastError = err; return 0; } // failed load -> handle 0, no error (Pathtracer.cpp:253-257)
 	return pt_load_texture_mem(c, img.width, img.height, img.isHdr ? 1 : 0, img.isHdr ? (const void *)img.hdr.data() : (const void *)img.ldr.data());
+	PT_CATCH(0u)
 }
 
 int pt_set_skybox(pt_context *c, uint32_t handle)
@@ -293,6 +326,7 @@ static SceneDev sceneDev(const pt_context *c)
 
 int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ignore_history)
 {
+	PT_TRY
 	if (!c || !camera) return setError(PT_E_INVALID, "pt_render: bad arguments");
 	CK(cudaSetDevice(c->device));
 	if (ignore_history)
@@ -304,10 +338,7 @@ int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ign
 	c->timingMs = 0.0f;
 	int launches = 0, usedSmem = 0;
 	CK(cudaMemsetAsync(c->counters, 0, kCtrCount * sizeof(unsigned long long), c->stream));
-	CK(cudaEventRecord(c->evStart, c->stream));
 	const bool run = c->nodeCount >= 1 && c->primCount >= 1 && spp > 0; // Pathtracer.cpp:174
-	// pixel partition: the pixels of the other ranks hold zeros, so that the sum over ranks is the image
-	if (run && ignore_history && c->pixelStride > 1u) CK(cudaMemsetAsync(c->accum, 0, size_t(c->width) * c->height * sizeof(float4), c->stream));
 	if (run)
 	{
 		RenderParams p;
@@ -327,43 +358,64 @@ int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ign
 		p.seedHi = uint32_t(c->seed >> 32);
 		p.maxBounces = c->maxBounces;
 		p.regenLow = c->launch.regenLow > 0 ? uint32_t(c->launch.regenLow) : (c->launch.variant == 8 || c->launch.variant == 9 || c->launch.variant == 10 ? 8u : 16u);
+		// first-bounce stratification (RenderParams::strataPer): 2^k cells, k <= 7, at least 32 samples per cell - a pass of the
+		// one-pixel-per-warp kernel then holds samples of one cell
+		const int v = c->launch.variant;
+		const bool perWarpKernel = v == 0 ? spp >= 64u : (v == 8 || v == 9 || v == 10 || v == 12 || v == 13); // launchTrace's choice
+		const bool wantStrata = perWarpKernel && (c->launch.stratify < 0 ? spp >= 128u : c->launch.stratify != 0) && spp >= 4u && spp < (1u << 21);
+		if (wantStrata)
+		{
+			uint32_t k = 2;
+			while (k < 7u && (spp >> (k + 1u)) >= 32u) ++k;
+			while (k > 2u && (spp >> k) == 0u) --k;
+			p.strataBitsA = (k + 1u) / 2u;
+			p.strataBitsB = k / 2u;
+			p.strataPer = spp >> k;
+			p.strataInvPer = 1.0f / float(p.strataPer);
+		}
+		p.sortScratch = nullptr;
+		p.sortStride = 0;
+		// round-1 alternative to the stratification: keep the plain Philox draws and SORT the pixel's samples by first scattering direction
+		const bool wantSort = !wantStrata && c->launch.sortSamples != 0 && spp <= 65535u && spp >= 64u;
+		if (wantSort)
 		{
 			// scratch for the per-pixel sample order: 2 x stride uint16 per warp of the (persistent) grid
-			const bool wantSort = (c->launch.sortSamples < 0 ? spp >= 1024u : c->launch.sortSamples != 0) && spp <= 65535u && spp >= 64u;
-			p.sortScratch = nullptr;
-			p.sortStride = 0;
-			if (wantSort)
+			const uint32_t stride = (spp + 127u) & ~127u;
+			const size_t warps = size_t(c->launch.smCount) * 2u * (1024u / 32u); // launchKernel: smCount x blocksPerSm (<= 2) CTAs of 32 warps
+			const size_t bytes = warps * size_t(stride) * (2u + 2u);             // order + keys per sample (sortSamples)
+			if (bytes > c->sortScratchBytes)
 			{
-				const uint32_t stride = (spp + 127u) & ~127u;
-				const size_t warps = size_t(c->launch.smCount) * 2u * (1024u / 32u); // launchKernel: smCount x blocksPerSm (<= 2) CTAs of 32 warps
-				const size_t bytes = warps * size_t(stride) * (2u + 2u);             // order + keys per sample (sortSamples)
-				if (bytes > c->sortScratchBytes)
-				{
-					if (c->sortScratch) CK(cudaFree(c->sortScratch));
-					c->sortScratch = nullptr;
-					c->sortScratchBytes = 0;
-					CK(cudaMalloc(&c->sortScratch, bytes));
-					c->sortScratchBytes = bytes;
-				}
-				p.sortScratch = static_cast<uint16_t *>(c->sortScratch);
-				p.sortStride = stride;
-				p.sortIgnore = c->launch.sortSamples == 2 ? 1u : 0u;
-				// measured on generated_scene (ms per 4096 spp): 64 bins 576, 128 bins (4 + 3 bits) 569, 256 bins 570-573; 2048 spp: 297 / 295
-				p.sortBitsA = c->launch.sortBitsA > 0 ? uint32_t(c->launch.sortBitsA) : 4u;
-				p.sortBitsB = c->launch.sortBitsB >= 0 ? uint32_t(c->launch.sortBitsB) : (spp >= 2048u ? 3u : 2u);
-				{
-					const uint32_t major = p.sortBitsA & 16u;
-					uint32_t a = p.sortBitsA & 15u, b = p.sortBitsB;
-					if (a + b < 5u) a = 5u - b;
-					if (a + b > 7u) { a = 4u; b = 3u; }
-					p.sortBitsA = a | major;
-					p.sortBitsB = b;
-				}
+				if (c->sortScratch) CK(cudaFree(c->sortScratch));
+				c->sortScratch = nullptr;
+				c->sortScratchBytes = 0;
+				CK(cudaMalloc(&c->sortScratch, bytes));
+				c->sortScratchBytes = bytes;
 			}
+			p.sortScratch = static_cast<uint16_t *>(c->sortScratch);
+			p.sortStride = stride;
+			p.sortIgnore = c->launch.sortSamples == 2 ? 1u : 0u;
+			// measured on generated_scene (ms per 4096 spp): 64 bins 576, 128 bins (4 + 3 bits) 569, 256 bins 570-573; 2048 spp: 297 / 295
+			p.sortBitsA = c->launch.sortBitsA > 0 ? uint32_t(c->launch.sortBitsA) : 4u;
+			p.sortBitsB = c->launch.sortBitsB >= 0 ? uint32_t(c->launch.sortBitsB) : (spp >= 2048u ? 3u : 2u);
+			const uint32_t major = p.sortBitsA & 16u;
+			uint32_t a = p.sortBitsA & 15u, b = p.sortBitsB;
+			if (a + b < 5u) a = 5u - b;
+			if (a + b > 7u) { a = 4u; b = 3u; }
+			p.sortBitsA = a | major;
+			p.sortBitsB = b;
 		}
 		p.beam = c->launch.beam < 0 ? (spp >= 128u ? 1u : 0u) : uint32_t(c->launch.beam != 0);
+		p.noJitter = c->noJitter ? 1u : 0u;
+		p.firstHitIndex = c->firstHit ? c->firstHitIndex : nullptr;
+		p.firstHitT = c->firstHit ? c->firstHitT : nullptr;
+		c->launch.stackLevels = int(c->bvhDepth) + 2;
+		CK(cudaEventRecord(c->evStart, c->stream)); // (all allocations are behind us: the events bracket the device work alone)
+		// pixel partition: the pixels of the other ranks hold zeros, so that the sum over ranks is the image
+		if (ignore_history && c->pixelStride > 1u) CK(cudaMemsetAsync(c->accum, 0, size_t(c->width) * c->height * sizeof(float4), c->stream));
 		launches = launchTrace(p, c->launch, c->stream, &usedSmem);
+		if (launches < 0) return setError(PT_E_CUDA, std::string("pt_render: kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
 	}
+	if (!run) CK(cudaEventRecord(c->evStart, c->stream));
 	CK(cudaEventRecord(c->evStop, c->stream));
 	CK(cudaGetLastError());
 	CK(cudaStreamSynchronize(c->stream));
@@ -378,7 +430,6 @@ int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ign
 			c->stats.samples = own * spp;
 		}
 		memcpy(c->rawCounters, h, sizeof h);
-		if (h[kCtrError] != 0) return setError(PT_E_CUDA, "pt_render: wavefront scheduler watchdog fired (code " + std::to_string(h[kCtrError]) + ")");
 		c->stats.rays = h[kCtrRays];
 		c->stats.node_visits = h[kCtrNodes];
 		c->stats.prim_tests = h[kCtrPrims];
@@ -394,6 +445,7 @@ int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ign
 	// call count as ceil(spp / k) calls so a single launch reproduces the reference CLI's 8-spp slicing (main.cpp:271-278)
 	c->accumulatedFrames += (c->framesPerSpp > 0) ? (spp + c->framesPerSpp - 1) / c->framesPerSpp : 1u;
 	return PT_OK;
+	PT_CATCH(PT_E_LIMIT)
 }
 
 float pt_get_timing_ms(const pt_context *c) { return c ? c->timingMs : 0.0f; }
@@ -424,6 +476,12 @@ const float *pt_get_hdr_mean(pt_context *c)
 	return readHdr(c, 1.0f / fmaxf(float(c->totalSamples), 1.0f));
 }
 
+const float *pt_get_hdr_sum(pt_context *c)
+{
+	if (!c) return nullptr;
+	return readHdr(c, 1.0f);
+}
+
 const uint8_t *pt_get_ldr(pt_context *c)
 {
 	if (!c) return nullptr;
@@ -443,10 +501,20 @@ const uint8_t *pt_get_ldr(pt_context *c)
 
 int pt_set_option(pt_context *c, const char *key, double value)
 {
+	PT_TRY
 	if (!c || !key) return setError(PT_E_INVALID, "pt_set_option: bad arguments");
 	const std::string k(key);
 	if (k == "seed") c->seed = uint64_t(value);
-	else if (k == "sample_offset") { c->sampleOffset = uint32_t(value); c->sampleCursor = c->sampleOffset; }
+	else if (k == "sample_offset")
+	{
+		// (setting the SAME offset again - a multi-GPU driver configuring its partition before every call - must not rewind
+		// the sample cursor of a progressive render: the next call would replay the same Philox indices)
+		if (uint32_t(value) != c->sampleOffset) { c->sampleOffset = uint32_t(value); c->sampleCursor = c->sampleOffset; }
+	}
+	// after a multi-GPU reduce the destination buffer holds the samples / frames of ALL ranks: let the driver say so, so that
+	// pt_get_hdr / pt_get_hdr_mean / pt_get_ldr normalise by the right count
+	else if (k == "total_samples") c->totalSamples = value < 0 ? 0ull : (unsigned long long)(value);
+	else if (k == "accumulated_frames") c->accumulatedFrames = value < 0 ? 0u : uint32_t(value);
 	else if (k == "sample_stride") c->sampleStride = value < 1 ? 1u : uint32_t(value);
 	else if (k == "pixel_offset") c->pixelOffset = value < 0 ? 0u : uint32_t(value);
 	else if (k == "pixel_stride") c->pixelStride = value < 1 ? 1u : uint32_t(value);
@@ -457,20 +525,31 @@ int pt_set_option(pt_context *c, const char *key, double value)
 	else if (k == "max_leaf") c->maxLeaf = value < 1 ? 1u : uint32_t(value);
 	else if (k == "variant") c->launch.variant = int(value);
 	else if (k == "max_global") c->maxGlobal = uint32_t(value < 0 ? 0 : value);
-	else if (k == "trace_low") c->launch.traceLow = int(value);
-	else if (k == "node_low") c->launch.nodeLow = int(value);
-	else if (k == "pool_warps") c->launch.poolWarps = int(value);
-	else if (k == "trace_warps") c->launch.traceWarps = int(value);
-	else if (k == "ready_low") c->launch.readyLow = int(value);
 	else if (k == "regen_low") c->launch.regenLow = int(value);
 	else if (k == "beam") c->launch.beam = int(value);
 	else if (k == "sort_samples") c->launch.sortSamples = int(value);
+	else if (k == "stratify") c->launch.stratify = int(value);
+	else if (k == "smem_stack") c->launch.smemStack = int(value);
+	else if (k == "jitter") c->noJitter = value == 0;
+	else if (k == "first_hit")
+	{
+		c->firstHit = value != 0;
+		if (c->firstHit && !c->firstHitIndex)
+		{
+			const size_t px = size_t(c->width) * c->height;
+			CK(cudaSetDevice(c->device));
+			CK(cudaMalloc(&c->firstHitIndex, px * 4));
+			CK(cudaMalloc(&c->firstHitT, px * 4));
+			CK(cudaMemset(c->firstHitIndex, 0xff, px * 4));
+			CK(cudaMemset(c->firstHitT, 0, px * 4));
+		}
+	}
 	else if (k == "sort_bits_a") c->launch.sortBitsA = int(value);
 	else if (k == "sort_bits_b") c->launch.sortBitsB = int(value);
 	else if (k == "tex_unit") { c->texUnit = value != 0; return uploadTextureTable(c); }
-	else if (k == "pool_slots") c->launch.poolSlots = int(value);
 	else return setError(PT_E_INVALID, "pt_set_option: unknown option " + k);
 	return PT_OK;
+	PT_CATCH(PT_E_LIMIT)
 }
 
 /* debugging aid (not in the header): raw device counters of the last pt_render, see trace_kernels.h kCtr* */
@@ -508,19 +587,16 @@ int pt_primary_pass(pt_context *c, const pt_camera_desc *camera, int32_t *hit_in
 		return PT_OK;
 	}
 	CK(cudaSetDevice(c->device));
-	int32_t *dIdx = nullptr;
-	float *dT = nullptr;
-	CK(cudaMalloc(&dIdx, px * 4));
-	CK(cudaMalloc(&dT, px * 4));
+	DevBuf dIdx, dT;
+	CK(dIdx.alloc(px * 4));
+	CK(dT.alloc(px * 4));
 	CameraDev cam;
 	computeCamera(*camera, cam);
-	launchPrimary(sceneDev(c), cam, c->width, c->height, dIdx, dT, c->stream);
+	launchPrimary(sceneDev(c), cam, c->width, c->height, dIdx.as<int32_t>(), dT.as<float>(), c->stream);
 	CK(cudaGetLastError());
-	CK(cudaMemcpyAsync(hit_index, dIdx, px * 4, cudaMemcpyDeviceToHost, c->stream));
-	CK(cudaMemcpyAsync(hit_t, dT, px * 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaMemcpyAsync(hit_index, dIdx.p, px * 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaMemcpyAsync(hit_t, dT.p, px * 4, cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
-	CK(cudaFree(dIdx));
-	CK(cudaFree(dT));
 	return PT_OK;
 }
 
@@ -530,20 +606,29 @@ int pt_trace_rays(pt_context *c, size_t n, const float *origins, const float *di
 	if (n == 0) return PT_OK;
 	if (c->nodeCount == 0) return setError(PT_E_INVALID, "pt_trace_rays: no scene");
 	CK(cudaSetDevice(c->device));
-	float *dO = nullptr, *dD = nullptr, *dT = nullptr, *dN = nullptr;
-	int32_t *dI = nullptr;
-	CK(cudaMalloc(&dO, n * 12)); CK(cudaMalloc(&dD, n * 12)); CK(cudaMalloc(&dT, n * 4)); CK(cudaMalloc(&dI, n * 4));
-	if (hit_normal) CK(cudaMalloc(&dN, n * 12));
-	CK(cudaMemcpyAsync(dO, origins, n * 12, cudaMemcpyHostToDevice, c->stream));
-	CK(cudaMemcpyAsync(dD, directions, n * 12, cudaMemcpyHostToDevice, c->stream));
-	launchTraceRays(sceneDev(c), n, dO, dD, t_min, dI, dT, dN, c->stream);
+	DevBuf dO, dD, dT, dI, dN;
+	CK(dO.alloc(n * 12)); CK(dD.alloc(n * 12)); CK(dT.alloc(n * 4)); CK(dI.alloc(n * 4));
+	if (hit_normal) CK(dN.alloc(n * 12));
+	CK(cudaMemcpyAsync(dO.p, origins, n * 12, cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(dD.p, directions, n * 12, cudaMemcpyHostToDevice, c->stream));
+	launchTraceRays(sceneDev(c), n, dO.as<float>(), dD.as<float>(), t_min, dI.as<int32_t>(), dT.as<float>(), dN.as<float>(), c->stream);
 	CK(cudaGetLastError());
-	CK(cudaMemcpyAsync(hit_index, dI, n * 4, cudaMemcpyDeviceToHost, c->stream));
-	CK(cudaMemcpyAsync(hit_t, dT, n * 4, cudaMemcpyDeviceToHost, c->stream));
-	if (hit_normal) CK(cudaMemcpyAsync(hit_normal, dN, n * 12, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaMemcpyAsync(hit_index, dI.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaMemcpyAsync(hit_t, dT.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+	if (hit_normal) CK(cudaMemcpyAsync(hit_normal, dN.p, n * 12, cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
-	cudaFree(dO); cudaFree(dD); cudaFree(dT); cudaFree(dI);
-	if (dN) cudaFree(dN);
+	return PT_OK;
+}
+
+int pt_get_first_hit(pt_context *c, int32_t *hit_index, float *hit_t)
+{
+	if (!c || !hit_index || !hit_t) return setError(PT_E_INVALID, "pt_get_first_hit: bad arguments");
+	if (!c->firstHitIndex) return setError(PT_E_INVALID, "pt_get_first_hit: option first_hit was not set before pt_render");
+	const size_t px = size_t(c->width) * c->height;
+	CK(cudaSetDevice(c->device));
+	CK(cudaMemcpyAsync(hit_index, c->firstHitIndex, px * 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaMemcpyAsync(hit_t, c->firstHitT, px * 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
 	return PT_OK;
 }
 
@@ -563,6 +648,7 @@ int pt_set_accum_device_ptr(pt_context *c, void *device_ptr)
 int pt_parse_scene_file(const char *json_path, pt_object_desc *objects, size_t capacity, pt_camera_desc *camera_out, float aspect, char *tex_paths,
                         size_t tex_paths_cap, int32_t *skybox_tex_index)
 {
+	PT_TRY
 	if (!json_path) return setError(PT_E_INVALID, "pt_parse_scene_file: null path");
 	ParsedScene ps;
 	std::string err;
@@ -579,10 +665,12 @@ int pt_parse_scene_file(const char *json_path, pt_object_desc *objects, size_t c
 		snprintf(tex_paths, tex_paths_cap, "%s", joined.c_str());
 	}
 	return int(ps.objects.size());
+	PT_CATCH(PT_E_LIMIT)
 }
 
 int pt_load_scene_file(pt_context *c, const char *json_path, pt_camera_desc *camera_out)
 {
+	PT_TRY
 	if (!c || !json_path) return setError(PT_E_INVALID, "pt_load_scene_file: bad arguments");
 	ParsedScene ps;
 	std::string err;
@@ -592,45 +680,44 @@ int pt_load_scene_file(pt_context *c, const char *json_path, pt_camera_desc *cam
 	// textures load in first-use order; a failed load maps to handle 0 and does not consume a slot (SceneLoader.cpp:127-149)
 	std::vector<uint32_t> handles(ps.texturePaths.size(), 0);
 	auto loadIdx = [&](uint32_t idx) -> uint32_t { return idx == 0 ? 0u : handles[idx - 1]; };
-	size_t objectTexCount = ps.texturePaths.size();
-	if (ps.skyboxTexture != 0 && ps.skyboxTexture == ps.texturePaths.size())
-	{
-		// the skybox path may be new (last entry) - it is loaded after setScene in the reference; handle order is the same
-	}
-	for (size_t i = 0; i < objectTexCount; ++i) handles[i] = pt_load_texture(c, ps.texturePaths[i].c_str());
+	for (size_t i = 0; i < ps.texturePaths.size(); ++i) handles[i] = pt_load_texture(c, ps.texturePaths[i].c_str());
 	for (pt_object_desc &o : ps.objects) o.material.texture = loadIdx(o.material.texture);
 	if (ps.hasObjectsArray)
 	{
 		const int r = pt_set_scene(c, ps.objects.size(), ps.objects.data());
 		if (r != PT_OK) return r;
 	}
-	if (ps.skyboxTexture != 0 || true)
-	{
-		// setSkyboxTextureHandle is only called when "skybox" is a string (SceneLoader.cpp:329-332); handle 0 otherwise
-		if (ps.skyboxTexture != 0) pt_set_skybox(c, loadIdx(ps.skyboxTexture));
-	}
+	// setSkyboxTextureHandle is called whenever "skybox" is a string (SceneLoader.cpp:327-332) - with handle 0 for "" or a
+	// failed load, so a context reused for another scene does not keep the previous sky
+	if (ps.hasSkyboxString) pt_set_skybox(c, loadIdx(ps.skyboxTexture));
 	if (camera_out) *camera_out = ps.camera;
 	return PT_OK;
+	PT_CATCH(PT_E_LIMIT)
 }
 
 int pt_write_png(const char *path, uint32_t width, uint32_t height, const uint8_t *rgba)
 {
+	PT_TRY
 	std::string err;
 	if (!path || !rgba) return setError(PT_E_INVALID, "pt_write_png: bad arguments");
 	if (!writePng(path, width, height, rgba, err)) return setError(PT_E_IO, err);
 	return PT_OK;
+	PT_CATCH(PT_E_LIMIT)
 }
 
 int pt_write_hdr(const char *path, uint32_t width, uint32_t height, const float *rgba)
 {
+	PT_TRY
 	std::string err;
 	if (!path || !rgba) return setError(PT_E_INVALID, "pt_write_hdr: bad arguments");
 	if (!writeHdr(path, width, height, rgba, err)) return setError(PT_E_IO, err);
 	return PT_OK;
+	PT_CATCH(PT_E_LIMIT)
 }
 
 int pt_read_image(const char *path, uint32_t *width, uint32_t *height, int *is_hdr, void **rgba)
 {
+	PT_TRY
 	if (!path || !width || !height || !is_hdr || !rgba) return setError(PT_E_INVALID, "pt_read_image: bad arguments");
 	Image img;
 	std::string err;
@@ -643,6 +730,7 @@ int pt_read_image(const char *path, uint32_t *width, uint32_t *height, int *is_h
 	if (!*rgba) return setError(PT_E_LIMIT, "pt_read_image: out of memory");
 	memcpy(*rgba, img.isHdr ? (const void *)img.hdr.data() : (const void *)img.ldr.data(), bytes);
 	return PT_OK;
+	PT_CATCH(PT_E_LIMIT)
 }
 
 } // extern "C"

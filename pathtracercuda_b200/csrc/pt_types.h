@@ -9,14 +9,15 @@ namespace ptb
 
 // One BVH node = the boxes of BOTH children + their references (64 B, one 128-bit x4 fetch tests two boxes).
 // Replaces the reference's 32 B single-box node (BVH.h:6-11), whose traversal needs one dependent fetch per box.
-//   f[0..2] = child0 box CENTRE, f[3..5] = child0 HALF EXTENT (padded outwards by a few ulp of the scene scale),
-//   f[6..8] / f[9..11] = the same for child1.  Centre/half-extent form turns the per-axis min/max pair of the slab test
-//   into FMAs: t_c = c*inv - o*inv, near = t_c - h*|inv|, far = t_c + h*|inv| (9 FMA + 4 min/max per box instead of
-//   6 FMA + 10 min/max: min/max issue at half rate on the ALU pipe, which is what bounded the node loop).
+//   Boxes are stored as CENTRE / HALF EXTENT (padded outwards by a few ulp of the scene scale): per axis
+//   t_c = c*inv - o*inv, near = t_c - h*|inv|, far = t_c + h*|inv| - FMAs instead of min/max pairs - and the two children
+//   are INTERLEAVED so that every 64-bit register pair of the 128-bit loads holds the same quantity of child 0 and child 1:
+//   sm_100's packed FFMA2 (fma.rn.f32x2) then does both children in ONE instruction (9 FFMA2 per node instead of 18 FFMA):
+//     f[0..5]  = (c0.x c1.x) (c0.y c1.y) (c0.z c1.z)      centres
+//     f[6..11] = (h0.x h1.x) (h0.y h1.y) (h0.z h1.z)      half extents          -> nodeF(child, half?, axis)
 //   child[k] >= 0 : index of an interior node
 //   child[k] <  0 : leaf; bits 0..23 = first primitive (BVH order), bits 24..27 = primitive count (1..15),
-//                   bits 28..30 = shape type of the first primitive (lets the scheduler bin the next intersection
-//                   by shape class without touching memory)
+//                   bits 28..30 = shape type of the first primitive
 //   an EMPTY child has child = kEmptyChild, centre +FLT_MAX and half extent -1 (near > far for every ray: never hit)
 struct alignas(16) Node
 {
@@ -25,6 +26,8 @@ struct alignas(16) Node
 	uint32_t pad[2];
 };
 static_assert(sizeof(Node) == 64, "Node must be 64 bytes");
+// index into Node::f of (child 0/1, centre (0) or half extent (1), axis 0..2)
+constexpr int nodeF(int child, int half, int axis) { return 6 * half + 2 * axis + child; }
 
 constexpr int32_t kLeafBit = int32_t(0x80000000u);
 constexpr int kLeafCountShift = 24;

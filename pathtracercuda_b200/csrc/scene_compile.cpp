@@ -284,6 +284,16 @@ struct Builder
 
 		if (n <= maxLeaf && ((bestAxis < 0 && isolate == end) || bestCost >= kPrimCost * float(n)))
 		{
+			// the primitives of a leaf in the order quadrics, flat shapes, cubes (the three branches of intersectLocal): the lanes
+			// of a warp that test their leaves' i-th primitives together then take the same branch more often.  (Ties are broken by
+			// scene index in the kernels, so the order inside a leaf cannot change a result.)
+			auto shapeClass = [this](const BuildPrim &p) -> int
+			{
+				const uint32_t t = objects[p.index].type;
+				return (t == PT_DISK || t == PT_QUAD) ? 1 : (t == PT_CUBE ? 2 : 0);
+			};
+			std::sort(bp.begin() + begin, bp.begin() + end, [&](const BuildPrim &a, const BuildPrim &b)
+				{ const int ca = shapeClass(a), cb2 = shapeClass(b); return ca < cb2 || (ca == cb2 && a.index < b.index); });
 			depth = 0;
 			leafCount++;
 			return leafRef(begin, n);
@@ -489,24 +499,29 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 		float scale = 0.0f;
 		for (int k = 0; k < 3; ++k) scale = std::max(scale, std::max(fabsf(sceneBox.mn[k]), fabsf(sceneBox.mx[k])));
 		for (Node &nd : out.nodes)
+		{
+			float mm[12]; // as the builder left them: child c = min[3] max[3] at 6 * c
+			memcpy(mm, nd.f, sizeof mm);
 			for (int c = 0; c < 2; ++c)
 			{
-				float *f = nd.f + 6 * c;
-				if (nd.child[c] == kEmptyChild)
-				{
-					for (int k = 0; k < 3; ++k) { f[k] = FLT_MAX; f[3 + k] = -1.0f; }
-					continue;
-				}
+				const float *f = mm + 6 * c;
 				for (int k = 0; k < 3; ++k)
 				{
+					if (nd.child[c] == kEmptyChild)
+					{
+						nd.f[nodeF(c, 0, k)] = FLT_MAX;
+						nd.f[nodeF(c, 1, k)] = -1.0f;
+						continue;
+					}
 					const double mn = f[k], mx = f[3 + k];
 					const float ctr = float(0.5 * (mn + mx));
 					double h = std::max(mx - double(ctr), double(ctr) - mn); // covers the rounding of the centre
 					h += 4.0e-7 * (fabs(double(ctr)) + h + double(scale)) + 1e-30;
-					f[k] = ctr;
-					f[3 + k] = nextafterf(float(h), FLT_MAX);
+					nd.f[nodeF(c, 0, k)] = ctr;                              // interleaved layout of pt_types.h
+					nd.f[nodeF(c, 1, k)] = nextafterf(float(h), FLT_MAX);
 				}
 			}
+		}
 	}
 	out.depth = depth;
 	out.leafCount = b.leafCount.load();

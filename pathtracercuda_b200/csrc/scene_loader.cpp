@@ -142,7 +142,7 @@ bool parseSceneText(const std::string &text, float aspect, ParsedScene &out, std
 	}
 
 	std::string sky;
-	if (getString(root, "skybox", sky)) out.skyboxTexture = textureHandle(sky);
+	if (getString(root, "skybox", sky)) { out.hasSkyboxString = true; out.skyboxTexture = textureHandle(sky); }
 
 	float position[3] = { 0.0f, 0.0f, 0.0f }, lookAt[3] = { 0.0f, 0.0f, -1.0f }, fovy = 60.0f;
 	const JsonValue *c = root.find("camera");

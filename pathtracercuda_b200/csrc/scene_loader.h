@@ -12,6 +12,7 @@ struct ParsedScene
 	std::vector<std::string> texturePaths;   // unique, in first-use order (objects first, then the skybox)
 	uint32_t skyboxTexture = 0;              // 1-based index into texturePaths, 0 = none
 	bool hasObjectsArray = false;
+	bool hasSkyboxString = false;            // "skybox" is a string: the loader calls setSkyboxTextureHandle (with 0 for "" or a failed load)
 	pt_camera_desc camera;
 	std::vector<std::string> messages;       // the loader's printf lines ("Failed to parse object type: ...")
 };

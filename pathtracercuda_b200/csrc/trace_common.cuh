@@ -1,4 +1,4 @@
-// trace_common.cuh — pieces shared by the trace kernels (trace_kernels.cu, trace_wavefront.cu).
+// trace_common.cuh — pieces shared by the trace kernels (trace_kernels.cu).
 #pragma once
 #define PTB_PRIM_FN __device__ __noinline__ // one out-of-line primitive test per kernel (code size, see trace_device.cuh)
 #define PTB_BEAM_FN __device__ __noinline__ // once per pixel: kept out of the hot loop's code

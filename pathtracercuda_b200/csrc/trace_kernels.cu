@@ -135,10 +135,12 @@ static __device__ __noinline__ void sortSamples(uint32_t pixel, const RenderPara
 // ---------------------------------------------------------------------------------------------------------------
 // the trace kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <bool SMEM, bool COUNT, int TRAV, bool SHARE, bool SPLIT = false>
+template <bool SMEM, bool COUNT, int TRAV, bool SHARE, bool SPLIT = false, bool SSTACK = false>
 __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_constant__ RenderParams p)
 {
 	extern __shared__ __align__(128) float4 smemScene[];
+	// SSTACK: this thread's column of the shared-memory traversal stack (trace_device.cuh TravStack<true>), behind the scene copy
+	const uint32_t stackColumn = SSTACK ? uint32_t(__cvta_generic_to_shared(smemScene)) + p.stackOffset + threadIdx.x * 4u : 0u;
 	__shared__ uint64_t mbar;
 	SceneView<SMEM> sv;
 	if constexpr (SMEM)
@@ -333,9 +335,23 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 					pixelToXY(pixel, p.width, p.height, px, py);
 					pxf = float(px); pyf = float(py);
 				}
-				const float u = (pxf + uniform01(r.x)) * invW; // trace.cu:190
-				const float v = (pyf + uniform01(r.y)) * invH;
+				float u = (pxf + uniform01(r.x)) * invW; // trace.cu:190
+				float v = (pyf + uniform01(r.y)) * invH;
+				if (p.noJitter) { u = divExact(pxf + 0.5f, float(p.width)); v = divExact(pyf + 0.5f, float(p.height)); } // the reference's primary-pass ray
 				rz = r.z; rw = r.w;
+				if constexpr (SHARE)
+				{
+					// first-bounce stratification: the cell of this sample (its local index / samples per cell) becomes the top bits of
+					// the two randoms of the first scattering direction, the Philox draw fills the bits below (RenderParams::strataPer)
+					if (sample < (p.strataPer << (p.strataBitsA + p.strataBitsB)))
+					{
+						const uint32_t cell = __float2uint_rz((__uint2float_rn(sample) + 0.5f) * p.strataInvPer);
+						const uint32_t a = cell >> p.strataBitsB, bMask = (1u << p.strataBitsB) - 1u;
+						const uint32_t b = (a & 1u) ? bMask - (cell & bMask) : (cell & bMask); // snake: neighbouring cells are neighbouring directions
+						rz = (a << (32u - p.strataBitsA)) | (rz >> p.strataBitsA);
+						rw = (b << (32u - p.strataBitsB)) | (rw >> p.strataBitsB);
+					}
+				}
 				ro = camO;
 				rd = cameraDir<kHotExact>(p.cam, u, v);
 				thr = mk(1.0f, 1.0f, 1.0f);
@@ -347,10 +363,16 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 			// ---- traverse + intersect (trace.cu:112) ----
 			++rays;
 			const Hit h = TRAV == 0 ? closestHit<SMEM, COUNT, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests)
-			              : TRAV == 1 ? closestHitWW<SMEM, COUNT, false, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? threadIdx.x >> 5 : 0],
-			                                                                        SHARE && bounce == 0 ? nBeam : -1)
-			                          : closestHitWW<SMEM, COUNT, true, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? threadIdx.x >> 5 : 0],
-			                                                                       SHARE && bounce == 0 ? nBeam : -1);
+			              : TRAV == 1 ? closestHitWW<SMEM, COUNT, false, kHotExact, SSTACK>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? threadIdx.x >> 5 : 0],
+			                                                                                SHARE && bounce == 0 ? nBeam : -1, stackColumn)
+			                          : closestHitWW<SMEM, COUNT, true, kHotExact, SSTACK>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? threadIdx.x >> 5 : 0],
+			                                                                               SHARE && bounce == 0 ? nBeam : -1, stackColumn);
+			if (bounce == 0 && p.firstHitIndex != nullptr)
+			{
+				// parity aid: what THIS kernel's traversal found for the camera ray (scene-order index, t), per pixel
+				p.firstHitIndex[pixel] = h.prim < 0 ? -1 : int32_t(__float_as_uint(sv.ld(sv.prims + h.prim * 4 + 3).y));
+				p.firstHitT[pixel] = h.prim < 0 ? 0.0f : h.t;
+			}
 
 			if constexpr (COUNT && SPLIT)
 			{
@@ -431,11 +453,11 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 	{
 		if (lane == 0)
 		{
-			for (int k = 0; k < 6; ++k) atomicAdd(&p.counters[kCtrTraceRounds + k], passStat[k]);
-			atomicAdd(&p.counters[kCtrTraceRounds + 6], (unsigned long long)(clock64() - kernelT0));
+			for (int k = 0; k < 6; ++k) atomicAdd(&p.counters[kCtrPassStats + k], passStat[k]);
+			atomicAdd(&p.counters[kCtrPassStats + 6], (unsigned long long)(clock64() - kernelT0));
 		}
-		atomicAdd(&p.counters[kCtrTraceRounds + 7], travClk[0]);
-		atomicAdd(&p.counters[kCtrTraceRounds + 8], travClk[1]);
+		atomicAdd(&p.counters[kCtrPassStats + 7], travClk[0]);
+		atomicAdd(&p.counters[kCtrPassStats + 8], travClk[1]);
 	}
 	if (COUNT)
 	{
@@ -523,54 +545,75 @@ __global__ void __launch_bounds__(kThreads) scaleKernel(const float4 *__restrict
 // ---------------------------------------------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------------------------------------------
+// Launch one persistent wave.  Returns the number of kernels launched (1), 0 when this instantiation cannot run with
+// `smemBytes` of dynamic shared memory (the caller then falls back to a configuration that needs less), -1 on a CUDA error.
 template <typename K>
 static int launchKernel(K kern, const RenderParams &p, const LaunchConfig &cfg, size_t smemBytes, cudaStream_t stream)
 {
-	if (smemBytes > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemBytes));
+	// opt in whenever dynamic shared memory is used: the 48 KB default limit covers static + dynamic together, and the
+	// one-pixel-per-warp kernels carry ~20 KB of static shared memory (beam lists, sort counters)
+	if (smemBytes > 0 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemBytes)) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return 0;
+	}
 	int blocksPerSm = 0;
-	cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, kern, kTraceThreads, smemBytes);
-	if (blocksPerSm < 1) blocksPerSm = 1;
+	if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, kern, kTraceThreads, smemBytes) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return 0;
+	}
+	if (blocksPerSm < 1) return 0;
 	const int grid = cfg.smCount * blocksPerSm;
 	kern<<<grid, kTraceThreads, smemBytes, stream>>>(p);
-	return 1;
+	return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
 }
 
-int launchTrace(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t stream, int *usedSmem)
+// static shared memory of the trace kernels (beam lists, per-warp pixel coordinates, sort counters, barrier) - an upper bound
+constexpr size_t kStaticSmemBound = 24576;
+
+int launchTrace(const RenderParams &pIn, const LaunchConfig &cfg, cudaStream_t stream, int *usedSmem)
 {
-	if (cfg.variant == 7)
-	{
-		const int n = launchTraceWavefront(p, cfg, stream, usedSmem);
-		if (n > 0) return n;
-	}
-	if (cfg.variant == 6 || cfg.variant == 7)
-	{
-		const int n = launchTraceWarpPool(p, cfg, stream, usedSmem);
-		if (n > 0) return n;
-	}
+	RenderParams p = pIn;
 	const size_t sceneBytes = (size_t(p.scene.nodeCount) + p.scene.primCount) * 64;
-	// leave room for 2+ CTAs per SM when the scene is small; a scene larger than the opt-in limit stays in L2/HBM
-	const bool smem = cfg.smemScene && sceneBytes + 24576 <= cfg.maxSmemOptin; // static shared memory: barrier + beam lists + sort counters
-	if (usedSmem) *usedSmem = smem ? 1 : 0;
-	const size_t sb = smem ? sceneBytes : 0;
+	int variant = cfg.variant;
+	// default: one pixel per warp (camera passes / scattered passes) for renders long enough to amortise the drain at the end of
+	// every pixel (the last paths of a pixel run with the other lanes idle: ~half a path per spp/32 samples), one pixel per lane otherwise
+	if (variant == 0) variant = p.spp >= 64 ? 12 : 4; // measured crossover on generated_scene: 32 spp 15.0 vs 15.2, 64 spp 15.7 vs 15.2, 128 spp 17.8 vs 15.2 Grays/s
+	const bool stackVariant = variant == 12 || variant == 4; // the two default kernels have shared-memory-stack instantiations
+	const size_t stackBytes = size_t(cfg.stackLevels) * kStackStride;
+	// what goes into shared memory: the scene when it fits (a scene larger than the opt-in limit stays in L2/HBM), the traversal
+	// stack when it fits beside it
+	bool smem = cfg.smemScene && sceneBytes + kStaticSmemBound <= cfg.maxSmemOptin;
+	bool sstack = stackVariant && cfg.smemStack != 0 && cfg.stackLevels > 0 && (smem ? sceneBytes : 0) + stackBytes + kStaticSmemBound <= cfg.maxSmemOptin;
 #define PT_PICK(KERN, ...)                                                                                                        \
 	(smem ? (cfg.countWork ? launchKernel(KERN<true, true __VA_ARGS__>, p, cfg, sb, stream) : launchKernel(KERN<true, false __VA_ARGS__>, p, cfg, sb, stream)) \
 	      : (cfg.countWork ? launchKernel(KERN<false, true __VA_ARGS__>, p, cfg, sb, stream) : launchKernel(KERN<false, false __VA_ARGS__>, p, cfg, sb, stream)))
-	// default: one pixel per warp (camera passes / scattered passes) for renders long enough to amortise the drain at the end of
-	// every pixel (the last paths of a pixel run with the other lanes idle: ~half a path per spp/32 samples), one pixel per lane otherwise
-	int variant = cfg.variant;
-	if (variant == 0) variant = p.spp >= 64 ? 12 : 4; // measured crossover on generated_scene: 32 spp 15.0 vs 15.2, 64 spp 15.7 vs 15.2, 128 spp 17.8 vs 15.2 Grays/s
-	switch (variant)
+	for (int attempt = 0; attempt < 3; ++attempt)
 	{
-	case 1: return PT_PICK(traceKernel, , 0, false);      // per-lane if/else traversal
-	case 5: return PT_PICK(traceKernel, , 2, false);      // while-while + speculative leaf parking
-	case 8: return PT_PICK(traceKernel, , 1, true);       // one pixel per WARP (lanes = samples), while-while
-	case 9: return PT_PICK(traceKernel, , 2, true);       // one pixel per warp, while-while + leaf parking
-	case 10: return PT_PICK(traceKernel, , 0, true);      // one pixel per warp, if/else traversal
-	case 12: return PT_PICK(traceKernel, , 1, true, true); // one pixel per warp, camera passes and scattered passes alternate
-	case 13: return PT_PICK(traceKernel, , 2, true, true); // 12 + leaf parking
-	default: return PT_PICK(traceKernel, , 1, false);     // 4: one pixel per lane, while-while traversal
+		if (usedSmem) *usedSmem = smem ? 1 : 0;
+		p.stackOffset = uint32_t(smem ? sceneBytes : 0); // records are 64 bytes: the stack starts 16-byte aligned
+		const size_t sb = (smem ? sceneBytes : 0) + (sstack ? stackBytes : 0);
+		int n;
+		switch (variant)
+		{
+		case 1: n = PT_PICK(traceKernel, , 0, false); break;      // per-lane if/else traversal
+		case 5: n = PT_PICK(traceKernel, , 2, false); break;      // while-while + speculative leaf parking
+		case 8: n = PT_PICK(traceKernel, , 1, true); break;       // one pixel per WARP (lanes = samples), while-while
+		case 9: n = PT_PICK(traceKernel, , 2, true); break;       // one pixel per warp, while-while + leaf parking
+		case 10: n = PT_PICK(traceKernel, , 0, true); break;      // one pixel per warp, if/else traversal
+		case 12: n = sstack ? PT_PICK(traceKernel, , 1, true, true, true) : PT_PICK(traceKernel, , 1, true, true); break; // one pixel per warp, camera passes and scattered passes alternate
+		case 13: n = PT_PICK(traceKernel, , 2, true, true); break; // 12 + leaf parking
+		default: n = sstack ? PT_PICK(traceKernel, , 1, false, false, true) : PT_PICK(traceKernel, , 1, false); break; // 4: one pixel per lane, while-while traversal
+		}
+		if (n != 0) return n;
+		// the instantiation does not fit with this much shared memory: first without the stack, then without the scene
+		if (sstack) sstack = false;
+		else if (smem) smem = false;
+		else return -1;
 	}
 #undef PT_PICK
+	return -1;
 }
 
 int launchPrimary(const SceneDev &scene, const CameraDev &cam, uint32_t width, uint32_t height, int32_t *hitIndex, float *hitT, cudaStream_t stream)

@@ -7,10 +7,10 @@ namespace ptb
 {
 
 // counters[] layout (device, unsigned long long)
-enum { kCtrWork = 0, kCtrRays = 1, kCtrNodes = 2, kCtrPrims = 3, kCtrShades = 4, kCtrMisses = 5, kCtrError = 7,
-       // scheduler statistics of the wavefront kernel (count_work = 1): stage executions and the slots they served
-       kCtrTraceRounds = 8, kCtrTraceWalkers = 9, kCtrNodeIters = 10, kCtrShadeExec = 11, kCtrShadeSlots = 12, kCtrGenExec = 13, kCtrGenSlots = 14,
-       kCtrLeafExec = 15, kCtrLeafSlots = 16, kCtrIdle = 17, kCtrBlocked = 18, kCtrRefills = 19, kCtrRefillSlots = 20, kCtrCount = 24 };
+enum { kCtrWork = 0, kCtrRays = 1, kCtrNodes = 2, kCtrPrims = 3, kCtrShades = 4, kCtrMisses = 5,
+       // pass statistics of the one-pixel-per-warp kernel (count_work = 1), 9 slots from kCtrPassStats: camera passes, their lanes,
+       // their clocks; scattered passes, lanes, clocks; kernel clocks; traversal clocks of camera / scattered passes
+       kCtrPassStats = 8, kCtrCount = 24 };
 
 struct SceneDev
 {
@@ -41,6 +41,18 @@ struct RenderParams
 	uint32_t sortIgnore = 0; // timing aid: sort, then hand the samples out in index order all the same
 	uint32_t sortBitsA = 4, sortBitsB = 2; // bins of the first / second random (2^(A+B) bins, 32..256)
 	uint32_t beam = 0;     // one-pixel-per-warp kernel: camera rays take their leaves from the pixel's beam list (trace_device.cuh)
+	// First-bounce stratification (one-pixel-per-warp kernels).  The launch's first strataPer << (strataBitsA + strataBitsB)
+	// samples of a pixel (local index m) take the first scattering direction's two randoms from cell m / strataPer of a
+	// 2^bitsA x 2^bitsB grid over the unit square (top bits = the cell, low bits = the Philox draw), so that (a) every cell gets
+	// exactly strataPer samples - stratified sampling of the first bounce, same expectation, never more variance - and (b) the
+	// lanes of a pass, which hold consecutive m, scatter into the SAME cell: what the sample sort bought, without sort, scratch
+	// or second Philox evaluation.  strataPer = 0: off.
+	uint32_t strataPer = 0, strataBitsA = 0, strataBitsB = 0;
+	float strataInvPer = 0.0f;
+	uint32_t noJitter = 0;          // parity aid: every sample through the pixel centre (u = (x + 0.5) / W, like the reference's primary pass)
+	int32_t *firstHitIndex = nullptr; // parity aid: scene index (-1: miss) and t of the camera ray's closest hit, per pixel, written by
+	float *firstHitT = nullptr;       // the render kernel itself (with noJitter every sample of a pixel writes the same values)
+	uint32_t stackOffset = 0;       // SSTACK kernels: byte offset of the shared-memory traversal stack in dynamic shared memory
 };
 
 struct LaunchConfig
@@ -50,25 +62,19 @@ struct LaunchConfig
 	int countWork = 0;   // node/prim/shade/miss counters
 	int variant = 0;     // kernel variant (0 = default: 12 for spp >= 64, else 4.  4: one pixel per lane, while-while traversal; 1: if/else traversal;
 	                     //  5: + leaf parking; 8: one pixel per WARP (lanes = samples), while-while; 9/10: its other traversals;
-	                     //  12: 8 with separate passes for camera rays and scattered rays;
-	                     //  6: warp-pool wavefront, 7: CTA-pool warp-specialised wavefront - both measured slower)
-	int traceLow = 0;    // warp-pool: run shade/generate early when fewer than this many lanes could traverse (0 = 24)
-	int nodeLow = 0;     // warp-pool: the node loop leaves when fewer than this many lanes are still walking (0 = 24)
-	int poolWarps = 0;   // warp-pool: warps per CTA (0 = as many as fit, <= 24)
-	int traceWarps = 0;  // wavefront: warps per CTA that only traverse (0 = half of them); the others run the other stages
-	int readyLow = -1;   // wavefront: stage warps run partial batches while the READY queue holds fewer rays than this (-1 = 128)
+	                     //  12: 8 with separate passes for camera rays and scattered rays)
 	int regenLow = 0;    // see RenderParams::regenLow (0 = default)
 	int sortBitsA = 0, sortBitsB = -1; // 0 / -1 = defaults
-	int sortSamples = -1; // order a pixel's samples by first scattering direction: 1 on, 0 off, -1 = on from 1024 spp (and spp <= 65535)
+	int sortSamples = 0; // order a pixel's samples by first scattering direction (round 1; superseded by `stratify`): 1 on, 0 off (default)
 	int beam = -1;       // pixel beams for the camera rays of the one-pixel-per-warp kernel: 1 on, 0 off, -1 = on from 128 spp
-	int poolSlots = 0;   // CTA-pool wavefront: path slots per CTA (0 = 1280 with the scene in shared memory, 1536 without)
+	int stratify = -1;   // first-bounce stratification (RenderParams::strataPer): 1 on, 0 off, -1 = on from 128 spp (one-pixel-per-warp kernels)
+	int smemStack = -1;  // traversal stack in shared memory (TravStack<true>): 1 on, 0 off, -1 = on when it fits beside the scene
+	int stackLevels = 0; // BVH depth + 2: levels the shared-memory stack needs (set by pt_render from the compiled scene)
 	size_t maxSmemOptin = 0;
 };
 
 // Returns the number of kernels launched; *usedSmem = 1 when the scene was staged in shared memory.
 int launchTrace(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t stream, int *usedSmem);
-int launchTraceWarpPool(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t stream, int *usedSmem);   // trace_warppool.cu; 0 = not applicable
-int launchTraceWavefront(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t stream, int *usedSmem); // trace_wavefront.cu; 0 = not applicable
 int launchPrimary(const SceneDev &scene, const CameraDev &cam, uint32_t width, uint32_t height, int32_t *hitIndex, float *hitT, cudaStream_t stream);
 int launchTraceRays(const SceneDev &scene, size_t n, const float *origins, const float *directions, float tMin, int32_t *hitIndex, float *hitT,
                     float *hitNormal, cudaStream_t stream);

@@ -106,9 +106,11 @@ def test_full_size_primary_properties():
 
 
 # ---- gate 2: path tracing ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("scene,W,H,spp", [("cornell_box", 64, 64, 64), ("generated_scene", 96, 54, 64)])
+@pytest.mark.parametrize("scene,W,H,spp", [("cornell_box", 64, 64, 64), ("generated_scene", 96, 54, 64), ("generated_scene", 80, 45, 320), ("cornell_box", 48, 48, 1100)])
 def test_render_matches_oracle_path_for_path(scene, W, H, spp):
-    """same Philox stream -> GPU and oracle trace the same paths; bit-level arithmetic differs, a few paths diverge"""
+    """same Philox stream -> GPU and oracle trace the same paths; bit-level arithmetic differs, a few paths diverge.  From 128 spp
+    both sides stratify the first scattering direction by the same integer rule (option "stratify", oracle/pt_oracle.c strataFor);
+    1100 spp = 64 cells of 17 samples + 12 unstratified ones"""
     earth, sky = _assets()
     objs, cam = _scene(scene, W, H)
     O = orc.Oracle(objs)
@@ -165,7 +167,7 @@ def test_kernel_variants_bit_identical():
             P.render(cam, spp, True)
             P.render(cam, spp, False)
             return P.getHDRMean()
-    imgs = {v: run(v, 16) for v in (1, 4, 5, 6, 7, 0)}
+    imgs = {v: run(v, 16) for v in (1, 4, 5, 0)}
     for v in imgs:
         assert np.array_equal(bits(imgs[1]), bits(imgs[v])), v
     # one pixel per warp: 80 samples = two full rounds of 32 + a ragged one; deterministic run to run; the default for spp >= 128
@@ -294,6 +296,7 @@ def test_sample_order_changes_nothing_but_the_order():
     def run(sort, **opts):
         with pt.Pathtracer(160, 90) as P:
             cam = P.loadSceneFile(f"{pt.ASSETS}/scenes/generated_scene.json", cwd=pt.ASSETS)
+            P.setOption("stratify", 0)  # the sort is the alternative to the stratification: plain Philox draws, ordered
             P.setOption("sort_samples", sort)
             for k, v in opts.items():
                 P.setOption(k, v)
@@ -309,6 +312,54 @@ def test_sample_order_changes_nothing_but_the_order():
     b2, r3 = run(1, sample_offset=3, sample_stride=4)
     assert r2 == r3 and np.allclose(a2, b2, rtol=3e-5, atol=1e-7) and not np.allclose(a, a2, rtol=1e-3)
     assert np.allclose(run(1, sort_bits_a=5, sort_bits_b=2)[0], a, rtol=3e-5, atol=1e-7)
+
+
+def test_first_bounce_stratification_is_unbiased_and_deterministic():
+    """option "stratify" (default from 128 spp): the cell of the first scattering direction comes from the sample's index, the
+    rest from Philox.  Same expectation as the plain draws: the two images agree within Monte Carlo noise (measured against
+    two plain renders with different seeds), the ray count within its own noise; bit-identical from run to run; and a render
+    too short for the default (64 spp) is untouched."""
+    def run(strat, seed=1984, spp=2048, W=160, H=90):
+        with pt.Pathtracer(W, H) as P:
+            cam = P.loadSceneFile(f"{pt.ASSETS}/scenes/generated_scene.json", cwd=pt.ASSETS)
+            P.setOption("stratify", strat)
+            P.setOption("seed", seed)
+            P.render(cam, spp, True)
+            return P.getHDRMean()[..., :3], P.stats().rays
+    plain_a, ra = run(0)
+    plain_b, rb = run(0, seed=7)
+    strat_a, rs = run(1)
+    strat_b, _ = run(-1)  # the default
+    strat_c, _ = run(1, seed=7)
+    assert np.array_equal(bits(strat_a), bits(strat_b)) and not np.array_equal(bits(strat_a), bits(plain_a))
+    floor = imgio.rmse(plain_a, plain_b)[0]
+    assert imgio.rmse(strat_a, plain_a)[0] <= 1.05 * floor and imgio.rmse(strat_a, plain_b)[0] <= 1.05 * floor
+    assert imgio.rmse(strat_a, strat_c)[0] <= 1.02 * floor  # never more variance than the plain draws
+    assert abs(strat_a.mean() / plain_a.mean() - 1) < 2e-3 and abs(rs / ra - 1) < 1e-3 and abs(rb / ra - 1) < 1e-3
+    assert np.array_equal(bits(run(-1, spp=64)[0]), bits(run(0, spp=64)[0]))
+
+
+def test_scene_sizes_around_the_shared_memory_opt_in_window():
+    """scenes of 150 ... 3200 objects: node + primitive records of 14 ... 300 KB.  Between 28 and 48 KB the scene fits the default
+    dynamic limit only without the kernels' ~20 KB of static shared memory (the opt-in has to be requested whenever dynamic
+    shared memory is used); around 130-200 KB the scene fits but scene + shared-memory stack may not; beyond ~200 KB it stays in
+    global memory.  Every size must render, finite, with the same rays per sample either way."""
+    W, H = 96, 54
+    for n in (150, 300, 400, 700, 1500, 3200):
+        objs, cam = scenegen.synthetic_scene(n, W, H)
+        res = []
+        for smem in (1, 0):
+            with pt.Pathtracer(W, H) as P:
+                P.setOption("smem_scene", smem)
+                P.setScene(objs)
+                P.render(cam, 8, True)     # one pixel per lane
+                st8 = P.stats()
+                P.render(cam, 160, True)   # one pixel per warp, beams, stratified
+                res.append((P.getHDRMean(), P.stats(), st8))
+        (a, sa, sa8), (b, sb, sb8) = res
+        assert np.isfinite(a).all() and sa.rays == sb.rays and sa8.rays == sb8.rays, n
+        assert sb.scene_in_smem == 0 and sa.scene_in_smem == (1 if n <= 1500 else 0), (n, sa.scene_bytes)
+        assert np.allclose(a, b, rtol=1e-4, atol=1e-5), n
 
 
 @pytest.mark.parametrize("spp", [24, 320])

@@ -201,6 +201,8 @@ def _validate_bvh(objs, max_leaf=4):
             first, count, typ = u & 0xffffff, (u >> 24) & 15, (u >> 28) & 7
             assert 1 <= count <= max(max_leaf, 1)
             assert typ == prims[first, 12]
+            cls = [1 if prims[k, 12] in (2, 5) else (2 if prims[k, 12] == 6 else 0) for k in range(first, first + count)]
+            assert cls == sorted(cls), "leaf primitives are ordered quadrics, flat shapes, cubes"
             b = np.array([[np.inf] * 3, [-np.inf] * 3])
             for k in range(first, first + count):
                 s = prims[k, 13]
@@ -216,7 +218,7 @@ def _validate_bvh(objs, max_leaf=4):
             if kids[c] == -2 ** 31:
                 continue
             b, d = walk(int(kids[c]), depth + 1)
-            ctr, half = n[6 * c:6 * c + 3].astype(np.float64), n[6 * c + 3:6 * c + 6].astype(np.float64)
+            ctr, half = n[[c, 2 + c, 4 + c]].astype(np.float64), n[[6 + c, 8 + c, 10 + c]].astype(np.float64)  # pt_types.h: children interleaved
             stored = np.array([ctr - half, ctr + half])      # nodes hold centre / (padded) half extent
             assert (half < (b[1] - b[0]) * 0.5 * (1 + 1e-5) + 1e-4).all(), "padding must stay tiny"
             assert (stored[0] <= b[0]).all() and (stored[1] >= b[1]).all(), "child box must contain its primitives"

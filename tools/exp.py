@@ -31,14 +31,3 @@ with pt.Pathtracer(W, H) as P:
                           "scattered_passes_per_ksample": round(1e3 * sp_ / st.samples, 2), "lanes_per_scattered_pass": round(sl / max(sp_, 1), 2), "clocks_per_scattered_pass": round(sc / max(sp_, 1), 1),
                           "share_camera": round(cc / tot, 3), "share_scattered": round(sc / tot, 3), "share_other": round(1 - (cc + sc) / tot, 3),
                           "traversal_share_of_camera_pass": round(raw[15] / max(cc, 1), 3), "traversal_share_of_scattered_pass": round(raw[16] / max(sc, 1), 3)}))
-    elif hasattr(P.L, "pt_debug_counters") and P.L.pt_debug_counters(P.h, raw, 24) == 24 and raw[8]:
-        r = list(raw)
-        names = ["traceRounds", "traceWalkers", "nodeIters", "shadeExec", "shadeSlots", "genExec", "genSlots", "leafExec", "leafSlots", "idle", "blocked", "refills", "refillSlots"]
-        d = dict(zip(names, r[8:21]))
-        rays = st.rays
-        print(json.dumps({"rays_per_traceRound": round(rays / max(d["traceRounds"], 1), 2), "walkers_at_round_start": round(d["traceWalkers"] / max(d["traceRounds"], 1), 2),
-                          "nodeIters_per_round": round(d["nodeIters"] / max(d["traceRounds"], 1), 2), "walkers_per_nodeIter": round(st.node_visits / max(d["nodeIters"], 1), 2),
-                          "shade_slots_per_exec": round(d["shadeSlots"] / max(d["shadeExec"], 1), 2), "gen_slots_per_exec": round(d["genSlots"] / max(d["genExec"], 1), 2),
-                          "leaf_slots_per_exec": round(d["leafSlots"] / max(d["leafExec"], 1), 2), "leaf_slots_per_ray": round(d["leafSlots"] / rays, 3),
-                          "idle_per_kray": round(1e3 * d["idle"] / rays, 3), "blocked_rounds_frac": round(d["blocked"] / max(d["traceRounds"], 1), 4),
-                          "refill_slots_per_refill": round(d["refillSlots"] / max(d["refills"], 1), 2), "raw": d}))

@@ -14,26 +14,11 @@ def marks(path, pats):
 K = marks(ROOT + "/pathtracercuda_b200/csrc/trace_kernels.cu", {
     "fetch": "// ---- accumulate + fetch the next pixel", "gen": "// ---- generate (trace.cu:187-192) ----", "trav": "// ---- traverse + intersect (trace.cu:112) ----",
     "miss": "// ---- environment miss (trace.cu:115-134) ----", "shade": "// ---- shade / sample (trace.cu:136-151) ----", "tail": "// ---- counters: one atomic per warp ----"})
-P = marks(ROOT + "/pathtracercuda_b200/csrc/trace_warppool.cu", {
-    "setup": "void __launch_bounds__(kPoolThreads, 1) traceKernelWP", "buildList": "auto buildList = ", "slotMask": "auto slotMask = ", "foldLeaf": "auto foldLeaf = ", "sched": "const int nIn = __popc(__ballot_sync(full, slot >= 0));",
-    "leaf": "// ---------------- deferred primitive tests", "shade": "// ---------------- shade / sample stage", "gen": "// ---------------- env-miss + accumulate + generate stage",
-    "refill": "// ---------------- BVH-traverse stage", "nodeloop": "// node loop: leaves when fewer than", "blocked": "// lanes holding a third leaf", "retire": "// retire finished traversals", "end": "#undef PF"})
 D = marks(ROOT + "/pathtracercuda_b200/csrc/trace_device.cuh", {
     "philox": "PTB_DEV uint4 philox4x32_10", "scene": "struct SceneView", "toLocal": "PTB_DEV void toLocal", "isect": "PTB_DEV bool intersectFlat", "trav": "struct TravRay", "testprim": "// One primitive against the ray, folded", "closest": "PTB_DEV Hit closestHit(",
     "surface": "struct Surface", "tex": "PTB_DEV float4 texel", "mat": "PTB_DEV V3 sampleVNDF", "cam": "PTB_DEV V3 cameraDir"})
-W = marks(ROOT + "/pathtracercuda_b200/csrc/trace_wavefront.cu", {
-    "setup": "void __launch_bounds__(kWfThreads, 1) traceKernelWF", "qPop": "auto qPop = ", "qPush": "auto qPush = ", "foldPrim": "auto foldPrim = ", "foldLeaf": "auto foldLeaf = ",
-    "inflight": "// ---- the lane's in-flight traversal ----", "park": "auto parkLeaves = ", "sched": "for (uint32_t iter = 0;; ++iter)", "refill": "// ---------------- BVH-traverse stage",
-    "nodeloop": "// node loop: leaves when fewer than", "blocked": "// lanes holding a third leaf", "retire": "// retire finished traversals", "leaf": "// ---------------- deferred primitive tests",
-    "shade": "// ---------------- shade / sample stage", "gen": "// ---------------- env-miss + accumulate + generate stage", "end": "#undef SF"})
 def bucket(f, l):
     l = int(l)
-    if f == "trace_wavefront.cu":
-        order = ["setup", "qPop", "qPush", "foldPrim", "foldLeaf", "inflight", "park", "sched", "refill", "nodeloop", "blocked", "retire", "leaf", "shade", "gen", "end"]
-        name = "wf_setup"
-        for n in order:
-            if n in W and l >= W[n]: name = "wf_" + n
-        return name
     if f == "trace_device.cuh":
         order = [("math", 0), ("philox", D["philox"]), ("ld", D["scene"]), ("toLocal", D["toLocal"]), ("intersect", D["isect"]), ("nodetest", D["trav"]), ("testPrim", D["testprim"]), ("closestHit*", D["closest"]),
                  ("surface", D["surface"]), ("tex", D["tex"]), ("material", D["mat"]), ("camera", D["cam"])]
@@ -45,11 +30,6 @@ def bucket(f, l):
         name = "k_setup"
         for n in ["fetch", "gen", "trav", "miss", "shade", "tail"]:
             if n in K and l >= K[n]: name = "k_" + n
-        return name
-    if f == "trace_warppool.cu":
-        name = "wp_setup"
-        for n in ["setup", "buildList", "slotMask", "foldLeaf", "sched", "leaf", "shade", "gen", "refill", "nodeloop", "blocked", "retire", "end"]:
-            if n in P and l >= P[n]: name = "wp_" + n
         return name
     return f
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
