@@ -86,6 +86,25 @@ int pt_create(uint32_t width, uint32_t height, int device, pt_context **out);
 /* Pathtracer::~Pathtracer   Pathtracer.cpp:70-109 */
 void pt_destroy(pt_context *ctx);
 
+/* Multi-GPU context (the reference is fixed to device 0, Pathtracer.cpp:40).  `device_mask` bit i = CUDA
+ * ordinal i; the lowest set bit is the ROOT device, whose buffers the image getters read.  The returned context is used
+ * with the SAME entry points as a single-device one: pt_set_scene builds the BVH once and replicates it, textures / skybox /
+ * options go to every device, pt_render splits the work and runs one host thread per GPU (blocking, like every call), the
+ * image getters, pt_get_timing_ms (slowest device + exchange) and pt_get_stats (sums) answer for the whole job.
+ * Options of a multi-GPU context:
+ *  "partition"  0 (default): PIXELS - device i renders all samples of the pixels i, i + N, ... (row-major); the image is
+ *               bit-identical to the single-GPU one.  1: SAMPLES - device i renders the global sample indices i, i + N, ... of
+ *               every pixel (north_star's split); equal up to float summation order (and to the per-launch stratification).
+ *  "exchange"   how the image comes together on the root.  1 / -1 (default, when the devices have peer access): pixel
+ *               partition only - the kernels of the other devices store their finished pixels directly into the root's
+ *               accumulation buffer over NVLink (16 B per pixel, no collective).  0: ONE ncclReduce (sum, float32, 4*W*H
+ *               elements) of the per-device accumulation buffers into a buffer on the root; always used by the sample
+ *               partition.  NCCL (libnccl.so.2) is loaded with dlopen the first time it is needed. */
+int pt_create_multi(uint32_t width, uint32_t height, uint32_t device_mask, pt_context **out);
+/* devices of the context (1 for pt_create), whether the last / next pt_render exchanges by peer-to-peer stores, and the two
+ * parts of pt_get_timing_ms of the last pt_render: slowest device's trace time, device time of the ncclReduce (0 with p2p). */
+int pt_get_multi_info(const pt_context *ctx, int *devices, int *peer_to_peer, float *trace_ms, float *exchange_ms);
+
 /* Pathtracer::setScene(count, hittables)   Pathtracer.h:22, Pathtracer.cpp:111-160.  Copies the input, builds the
  * BVH, replaces the previous scene.  count == 0 prints the reference's message and is a no-op returning PT_OK. */
 int pt_set_scene(pt_context *ctx, size_t count, const pt_object_desc *objects);
@@ -130,6 +149,8 @@ const float *pt_get_hdr_sum(pt_context *ctx);
  *                    so that the sum of the ranks' buffers is the image (default 0 / 1: every pixel)
  *  "total_samples" / "accumulated_frames"  overwrite the counts the image getters normalise by (after a multi-GPU reduce the
  *                    destination's buffer holds the samples of all ranks)
+ *  "alpha"           what pt_render writes into the fourth channel of the accumulation buffer (default 1, kernels/trace.cu:198); ranks > 0
+ *                    of a multi-process sample partition set 0 so that the reduced alpha is 1
  *  "frames_per_spp"  k>0: a pt_render of spp samples counts ceil(spp/k) frames for the Q1 normalisation
  *                    (k=8 reproduces the reference headless CLI, main.cpp:271-278); 0: one frame per call
  *  "count_work"      1: count node visits / primitive tests / shades / misses (slower)
@@ -141,7 +162,7 @@ const float *pt_get_hdr_sum(pt_context *ctx);
  *  "beam"            pixel beams for camera rays (one-pixel-per-warp kernels): 1 on, 0 off, -1 auto (default: on from 128 spp)
  *  "regen_low"       one-pixel-per-warp kernels: idle lanes wait until this many can start new samples together (0 = default)
  *  "stratify"        one-pixel-per-warp kernels: stratify the two randoms of the FIRST scattering direction over the samples of a
- *                    pixel (2^k cells of equal sample count, k <= 7; the cell is the top bits, the Philox draw the rest).  Same
+ *                    pixel (2^k cells of equal sample count, k <= 8; the cell is the top bits, the Philox draw the rest).  Same
  *                    expectation as the reference's plain draws (Material.inl:40-41), never more variance, and the lanes of a
  *                    warp scatter into the same cell (coherent traversal): 1 on, 0 off, -1 auto (default: on from 128 spp)
  *  "sort_samples"    alternative to "stratify" (used when that is off): hand a pixel's samples out in the order of their first

@@ -96,6 +96,14 @@ class Oracle:
         ok = self.L.orc_hit_object(self.s, i, _p(o), _p(d), tmin, tmax, _p(out))
         return (out if ok else None)
 
+    def decision_margin(self, i, o, d):
+        """how far the ray is from flipping a decision of object i's intersection routine, in units of float32 rounding noise"""
+        o = np.asarray(o, np.float32)
+        d = np.asarray(d, np.float32)
+        self.L.orc_decision_margin.restype = C.c_double
+        self.L.orc_decision_margin.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        return float(self.L.orc_decision_margin(self.s, i, _p(o), _p(d)))
+
     def material_sample(self, mat, N, in_dir, rnd0, rnd1):
         N = np.asarray(N, np.float32)
         in_dir = np.asarray(in_dir, np.float32)
@@ -129,6 +137,10 @@ class Oracle:
             accum = np.zeros((h, w, 4), np.float32)
         rays = self.L.orc_render(self.s, C.byref(cam), w, h, spp, seed, sample_offset, sample_stride, int(add), max_bounces, _p(accum))
         return accum, rays
+
+    def threads(self, n=0):
+        """OpenMP threads render() uses; n > 0 sets the count first"""
+        return int(self.L.orc_threads(int(n)))
 
     def tonemap(self, accum, sample_count):
         accum = np.ascontiguousarray(accum, np.float32)
@@ -175,6 +187,10 @@ class RefHost:
         L.refh_trace_rays.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refh_render.restype = C.c_uint64
         L.refh_render.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+
+    def threads(self, n=0):
+        """OpenMP threads render() uses; n > 0 sets the count first"""
+        return int(self.L.refh_threads(int(n)))
 
     def load_scene_file(self, path, w, h, cwd=None):
         old = os.getcwd()

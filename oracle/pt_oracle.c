@@ -726,6 +726,88 @@ int orc_hit_object(const orc_scene *s, size_t i, const float *o, const float *d,
 	out10[7] = rec.u; out10[8] = rec.v; out10[9] = rec.front ? 1.0f : 0.0f;
 	return 1;
 }
+/* How far a ray is from the nearest accept / reject DECISION of one object's intersection routine (Hittable.inl:147-358),
+ * in units of the rounding noise of the float32 evaluation.  Test infrastructure for the first-hit gate: two float32
+ * implementations of the same formulas (the reference's GPU build, ours with MUFU reciprocals) may only disagree about an
+ * object where this is small.  Computed in double precision from the object's world->local rows:
+ *   quadrics : tangency |disc| against the magnitude of its two terms b*b and 4*a*c (far from an object the local origin is
+ *              ~10^3 units away and the float32 discriminant has lost ~7 digits), and for the open quadrics the height test
+ *              |y| <= 1 at both roots against the magnitude of the terms of y = o.y + t * d.y
+ *   disk/quad: the edge tests at the plane hit against the magnitude of o + t * d;   cube: the slab interval's length
+ * Returns min over the decisions of |quantity - threshold| / (2^-23 * magnitude of the terms): < ~100 means "within float32
+ * rounding of flipping".  Also tMin / tMax are ignored (closest-hit competition between objects is judged by t). */
+double orc_decision_margin(const orc_scene *s, size_t i, const float *of, const float *df)
+{
+	const obj_t *ob = &s->sceneObjs[i];
+	const double eps = 1.1920929e-7;
+	double o[3], d[3], mo[3], md[3]; /* local origin / direction, and the magnitude of the terms that formed them */
+	const float *rows[3] = { ob->r0, ob->r1, ob->r2 };
+	for (int k = 0; k < 3; ++k)
+	{
+		const float *r = rows[k];
+		o[k] = (double)r[0] * of[0] + (double)r[1] * of[1] + (double)r[2] * of[2] + (double)r[3];
+		d[k] = (double)r[0] * df[0] + (double)r[1] * df[1] + (double)r[2] * df[2];
+		mo[k] = fabs((double)r[0] * of[0]) + fabs((double)r[1] * of[1]) + fabs((double)r[2] * of[2]) + fabs((double)r[3]);
+		md[k] = fabs((double)r[0] * df[0]) + fabs((double)r[1] * df[1]) + fabs((double)r[2] * df[2]);
+	}
+	double best = 1e300;
+#define MARGIN(q, mag) do { const double m_ = fabs(q) / (eps * ((mag) + 1e-300)); if (m_ < best) best = m_; } while (0)
+	const uint32_t type = ob->type;
+	if (type == PT_DISK || type == PT_QUAD)
+	{
+		if (d[1] == 0.0) return 0.0;
+		const double t = -o[1] / d[1];
+		const double hx = o[0] + d[0] * t, hz = o[2] + d[2] * t;
+		const double mx = mo[0] + fabs(d[0] * t) + md[0] * fabs(t), mz = mo[2] + fabs(d[2] * t) + md[2] * fabs(t);
+		if (type == PT_DISK) MARGIN(hx * hx + hz * hz - 1.0, 2.0 * (fabs(hx) * mx + fabs(hz) * mz) + 1.0);
+		else { MARGIN(fabs(hx) - 1.0, mx + 1.0); MARGIN(fabs(hz) - 1.0, mz + 1.0); }
+		MARGIN(t, fabs(t)); /* t == 0 never decides anything here; keeps best finite */
+		return best < 1e299 ? best : 1e299;
+	}
+	if (type == PT_CUBE)
+	{
+		double tn = -1e300, tf = 1e300, mag = 0.0;
+		for (int k = 0; k < 3; ++k)
+		{
+			if (d[k] == 0.0) continue;
+			double t0 = (-1.0 - o[k]) / d[k], t1 = (1.0 - o[k]) / d[k];
+			if (t0 > t1) { const double x = t0; t0 = t1; t1 = x; }
+			if (t0 > tn) tn = t0;
+			if (t1 < tf) tf = t1;
+			const double m = (mo[k] + 1.0) / fabs(d[k]) + fabs(t1) * md[k] / fabs(d[k]);
+			if (m > mag) mag = m;
+		}
+		MARGIN(tf - tn, mag);
+		return best;
+	}
+	const double B = type == PT_SPHERE ? 1.0 : (type == PT_CONE ? -1.0 : 0.0), Hc = type == PT_PARABOLOID ? -1.0 : 0.0;
+	const double J = (type == PT_SPHERE || type == PT_CYLINDER) ? -1.0 : 0.0;
+	const double a = d[0] * d[0] + B * d[1] * d[1] + d[2] * d[2];
+	const double b = 2.0 * (o[0] * d[0] + B * o[1] * d[1] + o[2] * d[2]) + Hc * d[1];
+	const double c = o[0] * o[0] + B * o[1] * o[1] + o[2] * o[2] + Hc * o[1] + J;
+	/* magnitudes of the float32 evaluations of b and c (their own terms cancel, then b*b - 4ac cancels again) */
+	const double mb = 2.0 * (fabs(o[0] * d[0]) + fabs(o[1] * d[1]) + fabs(o[2] * d[2])) + 2.0 * (mo[0] * fabs(d[0]) + mo[1] * fabs(d[1]) + mo[2] * fabs(d[2]));
+	const double mc = o[0] * o[0] + o[1] * o[1] + o[2] * o[2] + 2.0 * (mo[0] * fabs(o[0]) + mo[1] * fabs(o[1]) + mo[2] * fabs(o[2])) + 1.0;
+	const double disc = b * b - 4.0 * a * c;
+	MARGIN(disc, 2.0 * fabs(b) * mb + 4.0 * fabs(a) * mc + fabs(b * b) + fabs(4.0 * a * c));
+	if (disc >= 0.0 && type != PT_SPHERE && a != 0.0)
+	{
+		const double root = sqrt(disc);
+		const double q = b < 0.0 ? -0.5 * (b - root) : -0.5 * (b + root);
+		const double ts[2] = { q / a, q != 0.0 ? c / q : 0.0 };
+		/* the roots inherit the discriminant's noise through sqrt(disc): dt ~ d(disc) / (2 * root * 2a) */
+		const double dDisc = eps * (2.0 * fabs(b) * mb + 4.0 * fabs(a) * mc + fabs(b * b) + fabs(4.0 * a * c));
+		for (int k = 0; k < 2; ++k)
+		{
+			const double h = o[1] + d[1] * ts[k];
+			const double dt = root > 0.0 ? dDisc / (4.0 * fabs(a) * root) : 1e300;
+			const double magH = mo[1] + fabs(d[1] * ts[k]) + md[1] * fabs(ts[k]) + fabs(d[1]) * dt / eps + 1.0;
+			MARGIN(fabs(h) - 1.0, magH);
+		}
+	}
+#undef MARGIN
+	return best;
+}
 void orc_material_sample(const pt_material_desc *m, const float *N, const float *in_dir, float rnd0, float rnd1, float *out9)
 {
 	v3 sdir; float pdf;
@@ -766,6 +848,13 @@ void orc_trace_rays(const orc_scene *s, size_t n, const float *o, const float *d
  * need the checker to draw the same numbers.  The launch's first per << k samples of a pixel (local index i) take the two
  * randoms of the first scattering direction from cell i / per of a 2^bitsA x 2^bitsB grid: the cell gives the top bits, the
  * Philox draw the bits below.  Integer arithmetic only, so CPU and GPU agree to the bit.  Same rule as pt_render. */
+/* threads orc_render will use; n > 0 sets the count first (see refh_threads, oracle/ref_harness/ref_host.cpp) */
+#include <omp.h>
+int orc_threads(int n)
+{
+	if (n > 0) omp_set_num_threads(n);
+	return omp_get_max_threads();
+}
 static int g_stratify = 0;
 void orc_set_stratify(int on) { g_stratify = on; }
 static void strataFor(uint32_t spp, uint32_t *per, uint32_t *bitsA, uint32_t *bitsB)
@@ -773,7 +862,7 @@ static void strataFor(uint32_t spp, uint32_t *per, uint32_t *bitsA, uint32_t *bi
 	*per = 0; *bitsA = *bitsB = 0;
 	if (!g_stratify || spp < 4u || spp >= (1u << 21)) return;
 	uint32_t k = 2;
-	while (k < 7u && (spp >> (k + 1u)) >= 32u) ++k;
+	while (k < 8u && (spp >> (k + 1u)) >= 16u) ++k;
 	while (k > 2u && (spp >> k) == 0u) --k;
 	*bitsA = (k + 1u) / 2u; *bitsB = k / 2u; *per = spp >> k;
 }

@@ -27,7 +27,10 @@ void orc_trace_rays(const orc_scene *s, size_t n, const float *o, const float *d
 uint64_t orc_render(const orc_scene *s, const pt_camera_desc *cam, uint32_t w, uint32_t h, uint32_t spp, uint64_t seed,
                     uint32_t sample_offset, uint32_t sample_stride, int add, int max_bounces, float *accum);
 /* first-bounce stratification of the product's one-pixel-per-warp kernels (not in the reference; see pt_oracle.c) */
+/* distance of a ray from the nearest accept / reject decision of one object, in units of float32 rounding noise (test aid) */
+double orc_decision_margin(const orc_scene *s, size_t i, const float *o, const float *d);
 void orc_set_stratify(int on);
+int orc_threads(int n);
 void orc_tonemap(const float *accum, size_t pixels, uint32_t sample_count, uint8_t *out);
 void orc_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t *out4);
 float orc_uniform(uint32_t x);

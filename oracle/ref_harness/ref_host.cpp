@@ -186,6 +186,7 @@ namespace
 	}
 }
 
+#include <omp.h>
 extern "C"
 {
 	// --- scene input -------------------------------------------------------------------------------------
@@ -375,6 +376,13 @@ extern "C"
 
 	// full path tracing on the host following kernels/trace.cu:158-199 (XORWOW seed = seedBase + pixel, as
 	// kernels/initRandState.cu:16).  accum = SUM over spp samples (RGBA, A = 1).  Returns rays traced.
+	// threads the next refh_render will use (bench.py reports them as cpu_baseline.cores); n > 0 sets the count first -
+	// torchrun exports OMP_NUM_THREADS=1 to its workers, which would time one core and call it the box
+	int refh_threads(int n)
+	{
+		if (n > 0) omp_set_num_threads(n);
+		return omp_get_max_threads();
+	}
 	uint64_t refh_render(uint32_t width, uint32_t height, uint32_t spp, uint32_t seedBase, float *accumRGBA)
 	{
 		uint64_t rays = 0;

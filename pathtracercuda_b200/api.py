@@ -26,6 +26,8 @@ def load_library():
     vp, u32, i32, f32, sz, cp = C.c_void_p, C.c_uint32, C.c_int, C.c_float, C.c_size_t, C.c_char_p
     sig = {
         "pt_create": (i32, [u32, u32, i32, C.POINTER(vp)]),
+        "pt_create_multi": (i32, [u32, u32, u32, C.POINTER(vp)]),
+        "pt_get_multi_info": (i32, [vp, vp, vp, vp, vp]),
         "pt_destroy": (None, [vp]),
         "pt_set_scene": (i32, [vp, sz, vp]),
         "pt_load_texture": (u32, [vp, cp]),
@@ -63,7 +65,7 @@ def load_library():
     return L
 
 
-EXPORTS = ["pt_create", "pt_destroy", "pt_set_scene", "pt_load_texture", "pt_load_texture_mem", "pt_set_skybox", "pt_render",
+EXPORTS = ["pt_create", "pt_create_multi", "pt_get_multi_info", "pt_destroy", "pt_set_scene", "pt_load_texture", "pt_load_texture_mem", "pt_set_skybox", "pt_render",
            "pt_get_timing_ms", "pt_get_hdr", "pt_get_hdr_mean", "pt_get_hdr_sum", "pt_get_ldr", "pt_set_option", "pt_get_stats", "pt_camera_rotate", "pt_camera_translate", "pt_primary_pass",
            "pt_trace_rays", "pt_get_first_hit", "pt_accum_device_ptr", "pt_set_accum_device_ptr", "pt_load_scene_file", "pt_parse_scene_file",
            "pt_write_png", "pt_write_hdr", "pt_read_image", "pt_free", "pt_last_error", "pt_version"]
@@ -143,13 +145,23 @@ class Pathtracer:
     getTiming, loadTexture, setSkyboxTextureHandle, getHDRImageData, getImageData) keep the reference's argument
     meaning; the rest are the extensions of include/pt_b200.h."""
 
-    def __init__(self, width, height, device=0):
+    def __init__(self, width, height, device=0, device_mask=0):
+        """device_mask != 0: a multi-GPU context over these CUDA ordinals (pt_create_multi) - same methods"""
         self.L = load_library()
         self.width, self.height = int(width), int(height)
         h = C.c_void_p()
-        _check(self.L, self.L.pt_create(self.width, self.height, int(device), C.byref(h)), "pt_create")
+        if device_mask:
+            _check(self.L, self.L.pt_create_multi(self.width, self.height, int(device_mask), C.byref(h)), "pt_create_multi")
+        else:
+            _check(self.L, self.L.pt_create(self.width, self.height, int(device), C.byref(h)), "pt_create")
         self.h = h
         self._objs = None
+
+    def multiInfo(self):
+        """(devices, peer_to_peer, trace_ms, exchange_ms) of the last render (pt_get_multi_info)"""
+        n, p2p, tr, ex = C.c_int(), C.c_int(), C.c_float(), C.c_float()
+        _check(self.L, self.L.pt_get_multi_info(self.h, C.byref(n), C.byref(p2p), C.byref(tr), C.byref(ex)), "pt_get_multi_info")
+        return n.value, bool(p2p.value), tr.value, ex.value
 
     def close(self):
         if getattr(self, "h", None):

@@ -3,7 +3,8 @@
 // same output files.  The windowed branch (-window / -enable_controls, main.cpp:298-437) needs GLFW/OpenGL and is
 // out of scope on a headless B200 server: the flags are parsed and reported, then refused.
 // Extra options use a double dash so they cannot collide with the reference's: --device N, --seed S, --slice N,
-// --true-mean, --stats.
+// --true-mean, --stats, and for several GPUs of one box (the reference is fixed to device 0, Pathtracer.cpp:40):
+// --gpus N (devices 0..N-1) or --devices MASK, --partition pixels|samples, --exchange p2p|nccl (pt_create_multi).
 #include "../../include/pt_b200.h"
 #include <algorithm>
 #include <cstdio>
@@ -26,6 +27,9 @@ struct Params // reference Params.h:4-14
 	unsigned int slice = 0; // samples per launch; 0 = all in one launch
 	bool trueMean = false;
 	bool stats = false;
+	unsigned int deviceMask = 0; // != 0: multi-GPU context over these CUDA ordinals
+	int partition = 0;           // 0 pixels, 1 samples
+	int exchange = -1;           // -1 auto, 0 nccl, 1 p2p
 };
 
 static bool processArgs(int argc, char *argv[], Params &params)
@@ -62,6 +66,10 @@ static bool processArgs(int argc, char *argv[], Params &params)
 		else if (strcmp(a, "--device") == 0 && i + 1 < argc) { params.device = atoi(argv[i + 1]); i += 2; }
 		else if (strcmp(a, "--seed") == 0 && i + 1 < argc) { params.seed = strtoull(argv[i + 1], nullptr, 10); i += 2; }
 		else if (strcmp(a, "--slice") == 0 && i + 1 < argc) { params.slice = (unsigned int)atoi(argv[i + 1]); i += 2; }
+		else if (strcmp(a, "--gpus") == 0 && i + 1 < argc) { const int n = atoi(argv[i + 1]); params.deviceMask = n >= 32 ? 0xffffffffu : (n > 0 ? (1u << n) - 1u : 0u); i += 2; }
+		else if (strcmp(a, "--devices") == 0 && i + 1 < argc) { params.deviceMask = (unsigned int)strtoul(argv[i + 1], nullptr, 0); i += 2; }
+		else if (strcmp(a, "--partition") == 0 && i + 1 < argc) { params.partition = strcmp(argv[i + 1], "samples") == 0 ? 1 : 0; i += 2; }
+		else if (strcmp(a, "--exchange") == 0 && i + 1 < argc) { params.exchange = strcmp(argv[i + 1], "nccl") == 0 ? 0 : (strcmp(argv[i + 1], "p2p") == 0 ? 1 : -1); i += 2; }
 		else if (strcmp(a, "--true-mean") == 0) { params.trueMean = true; ++i; }
 		else if (strcmp(a, "--stats") == 0) { params.stats = true; ++i; }
 		else
@@ -126,7 +134,13 @@ int main(int argc, char *argv[])
 	}
 
 	pt_context *ctx = nullptr;
-	if (pt_create(params.m_width, params.m_height, params.device, &ctx) != PT_OK) die("pt_create");
+	if (params.deviceMask != 0)
+	{
+		if (pt_create_multi(params.m_width, params.m_height, params.deviceMask, &ctx) != PT_OK) die("pt_create_multi");
+		pt_set_option(ctx, "partition", (double)params.partition);
+		pt_set_option(ctx, "exchange", (double)params.exchange);
+	}
+	else if (pt_create(params.m_width, params.m_height, params.device, &ctx) != PT_OK) die("pt_create");
 	pt_set_option(ctx, "seed", (double)params.seed);
 	// reference-compatible normalisation: the reference renders 8 samples per render() call and divides by the number
 	// of CALLS (quirk Q1); one launch here counts as ceil(spp/8) calls.  --true-mean writes the real mean instead.
@@ -139,7 +153,8 @@ int main(int argc, char *argv[])
 	if (lr != PT_OK) die("pt_load_scene_file");
 
 	const unsigned int slice = params.slice ? params.slice : params.m_spp;
-	float totalGpuTime = 0.0f;
+	float totalGpuTime = 0.0f, totalTrace = 0.0f, totalExchange = 0.0f;
+	unsigned long long totalRays = 0;
 	unsigned int nextReport = 0;
 	for (unsigned int i = 0; i < params.m_spp; i += slice)
 	{
@@ -148,14 +163,26 @@ int main(int argc, char *argv[])
 		for (; nextReport < i + spp; nextReport += 32) printf("Accumulated %d samples\n", (int)nextReport);
 		if (pt_render(ctx, &camera, spp, i == 0) != PT_OK) die("pt_render");
 		totalGpuTime += pt_get_timing_ms(ctx);
+		float tr = 0.0f, ex = 0.0f;
+		pt_get_multi_info(ctx, nullptr, nullptr, &tr, &ex);
+		totalTrace += tr;
+		totalExchange += ex;
+		pt_stats st;
+		pt_get_stats(ctx, &st);
+		totalRays += st.rays;
 	}
 	printf("Finished accumulating %d samples in %f ms GPU time\n", (int)params.m_spp, totalGpuTime);
 	if (params.stats)
 	{
 		pt_stats st;
 		pt_get_stats(ctx, &st);
-		printf("{\"rays_last_launch\": %llu, \"samples_last_launch\": %llu, \"bvh_nodes\": %u, \"bvh_depth\": %u, \"scene_bytes\": %u, \"scene_in_smem\": %u}\n",
-		       (unsigned long long)st.rays, (unsigned long long)st.samples, st.bvh_nodes, st.bvh_depth, st.scene_bytes, st.scene_in_smem);
+		int devices = 1, p2p = 0;
+		pt_get_multi_info(ctx, &devices, &p2p, nullptr, nullptr);
+		printf("{\"rays\": %llu, \"rays_last_launch\": %llu, \"samples_last_launch\": %llu, \"bvh_nodes\": %u, \"bvh_depth\": %u, \"scene_bytes\": %u, \"scene_in_smem\": %u, "
+		       "\"devices\": %d, \"partition\": \"%s\", \"exchange\": \"%s\", \"trace_ms\": %f, \"exchange_ms\": %f, \"exchange_bytes_per_device\": %llu}\n",
+		       totalRays, (unsigned long long)st.rays, (unsigned long long)st.samples, st.bvh_nodes, st.bvh_depth, st.scene_bytes, st.scene_in_smem, devices,
+		       params.partition ? "samples" : "pixels", devices == 1 ? "none" : (p2p ? "p2p" : "nccl"), totalTrace, totalExchange,
+		       (unsigned long long)(devices == 1 ? 0ull : (p2p ? (unsigned long long)params.m_width * params.m_height * 16ull / devices : (unsigned long long)params.m_width * params.m_height * 16ull)));
 	}
 
 	if (params.m_outputFilepath)

@@ -9,7 +9,10 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace ptb;
@@ -67,6 +70,24 @@ struct pt_context
 	LaunchConfig launch;
 	pt_stats stats;
 	unsigned long long rawCounters[ptb::kCtrCount] = {};
+	// ---- multi-GPU (pt_create_multi).  This context is the ROOT: the first device of the mask, the one whose buffers the
+	// image getters read.  `peers` are ordinary single-device contexts on the other devices; every call on the root is
+	// carried out on all of them (scene, textures, options) or split over them (pt_render, one host thread per GPU).
+	std::vector<pt_context *> peers;
+	int partition = 0;            // how pt_render splits the work: 0 = pixels (device i: pixels i, i + N, ...), 1 = samples
+	int exchange = -1;            // how the image comes together: 1 = peer-to-peer stores into the root's buffer (pixels only),
+	                              // 0 = one ncclReduce of the float4 accumulation buffers, -1 = p2p when the devices allow it
+	bool p2pReady = false;        // peer access root <- peers enabled
+	struct NcclState *nccl = nullptr;
+	float4 *reduced = nullptr;    // NCCL exchange: the sum over devices lands here (the per-device partial sums stay intact)
+	const float4 *imageSource = nullptr; // what the image getters read: null = accum
+	float reduceMs = 0.0f;        // device time of the last exchange (0 with peer-to-peer stores: there is none)
+	unsigned long long jobSamples = 0; // samples per pixel / render calls of the whole job since the last restart
+	uint32_t jobFrames = 0;
+	float multiTraceMs = 0.0f;    // slowest device's trace time of the last pt_render
+	pt_stats multiStats = {};     // statistics of the last pt_render summed over the devices
+	float alpha = 1.0f;           // RenderParams::alpha
+	bool skipPartitionClear = false; // p2p: the other devices write their pixels into this very buffer - nothing to zero
 };
 
 #define CK(expr)                                                                                                      \
@@ -92,6 +113,23 @@ struct DevBuf
 	template <typename T> T *as() const { return static_cast<T *>(p); }
 };
 } // namespace
+
+// NCCL is loaded at run time (dlopen, local scope), only when a multi-GPU context first needs a reduce: the library keeps
+// no link-time dependency on it - a host process that already carries its own NCCL (PyTorch's) is left alone, and single-GPU
+// users need none.  <nccl.h> is used for its types only.
+struct NcclState
+{
+	void *lib = nullptr;
+	ncclResult_t (*commInitAll)(ncclComm_t *, int, const int *) = nullptr;
+	ncclResult_t (*commDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*groupStart)() = nullptr;
+	ncclResult_t (*groupEnd)() = nullptr;
+	ncclResult_t (*reduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	const char *(*getErrorString)(ncclResult_t) = nullptr;
+	std::vector<ncclComm_t> comms;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr; // on the root's stream, around the reduce
+	bool warm = false;                        // the communicators have run their first collective
+};
 
 // No C++ exception may cross the C boundary (std::bad_alloc from a huge scene or image would otherwise terminate the host)
 #define PT_TRY try {
@@ -152,10 +190,71 @@ int pt_create(uint32_t width, uint32_t height, int device, pt_context **out)
 	PT_CATCH(PT_E_LIMIT)
 }
 
+int pt_create_multi(uint32_t width, uint32_t height, uint32_t device_mask, pt_context **out)
+{
+	PT_TRY
+	if (!out || device_mask == 0) return setError(PT_E_INVALID, "pt_create_multi: bad arguments");
+	*out = nullptr;
+	std::vector<int> devs;
+	for (int d = 0; d < 32; ++d)
+		if (device_mask & (1u << d)) devs.push_back(d);
+	pt_context *root = nullptr;
+	int r = pt_create(width, height, devs[0], &root);
+	if (r != PT_OK) return r;
+	for (size_t i = 1; i < devs.size(); ++i)
+	{
+		pt_context *peer = nullptr;
+		r = pt_create(width, height, devs[i], &peer);
+		if (r != PT_OK) { const std::string e = g_lastError; pt_destroy(root); g_lastError = e; return r; }
+		root->peers.push_back(peer);
+	}
+	// peer access root <- every other device: their kernels can then store finished pixels straight into the root's buffer
+	root->p2pReady = !root->peers.empty();
+	for (pt_context *peer : root->peers)
+	{
+		int can = 0;
+		if (cudaSetDevice(peer->device) != cudaSuccess || cudaDeviceCanAccessPeer(&can, peer->device, root->device) != cudaSuccess || !can) { root->p2pReady = false; continue; }
+		const cudaError_t e = cudaDeviceEnablePeerAccess(root->device, 0);
+		if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) root->p2pReady = false;
+		cudaGetLastError();
+	}
+	cudaSetDevice(root->device);
+	*out = root;
+	return PT_OK;
+	PT_CATCH(PT_E_LIMIT)
+}
+
+int pt_get_multi_info(const pt_context *c, int *devices, int *peer_to_peer, float *trace_ms, float *exchange_ms)
+{
+	if (!c) return setError(PT_E_INVALID, "pt_get_multi_info: null context");
+	if (devices) *devices = int(c->peers.size()) + 1;
+	if (peer_to_peer) *peer_to_peer = (c->partition == 0 && c->p2pReady && c->exchange != 0) ? 1 : 0;
+	if (trace_ms) *trace_ms = c->peers.empty() ? c->timingMs : c->multiTraceMs;
+	if (exchange_ms) *exchange_ms = c->reduceMs;
+	return PT_OK;
+}
+
 void pt_destroy(pt_context *c)
 {
 	if (!c) return;
+	for (pt_context *peer : c->peers)
+	{
+		if (peer->accum == c->accum) { peer->accum = nullptr; peer->ownAccum = false; } // p2p: the buffer is the root's
+		pt_destroy(peer);
+	}
+	c->peers.clear();
+	if (c->nccl)
+	{
+		for (ncclComm_t comm : c->nccl->comms) if (comm && c->nccl->commDestroy) c->nccl->commDestroy(comm);
+		cudaSetDevice(c->device);
+		if (c->nccl->ev0) cudaEventDestroy(c->nccl->ev0);
+		if (c->nccl->ev1) cudaEventDestroy(c->nccl->ev1);
+		if (c->nccl->lib) dlclose(c->nccl->lib);
+		delete c->nccl;
+		c->nccl = nullptr;
+	}
 	cudaSetDevice(c->device);
+	if (c->reduced) cudaFree(c->reduced);
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	if (c->ownAccum && c->accum) cudaFree(c->accum);
 	if (c->scaledDev) cudaFree(c->scaledDev);
@@ -178,19 +277,9 @@ void pt_destroy(pt_context *c)
 	delete c;
 }
 
-int pt_set_scene(pt_context *c, size_t count, const pt_object_desc *objects)
+// upload a compiled scene to one device (replaces the previous one)
+static int uploadScene(pt_context *c, const CompiledScene &cs)
 {
-	PT_TRY
-	if (!c) return setError(PT_E_INVALID, "pt_set_scene: null context");
-	if (count == 0)
-	{
-		printf("Setting an empty scene is not allowed!\n"); // Pathtracer.cpp:115
-		return PT_OK;
-	}
-	if (!objects) return setError(PT_E_INVALID, "pt_set_scene: null objects");
-	CompiledScene cs;
-	std::string err;
-	if (!compileScene(count, objects, c->maxLeaf, cs, err, c->maxGlobal)) return setError(PT_E_LIMIT, "pt_set_scene: " + err);
 	CK(cudaSetDevice(c->device));
 	CK(cudaStreamSynchronize(c->stream));
 	if (c->sceneBlob) { CK(cudaFree(c->sceneBlob)); c->sceneBlob = nullptr; }
@@ -211,6 +300,25 @@ int pt_set_scene(pt_context *c, size_t count, const pt_object_desc *objects)
 	c->stats.bvh_depth = c->bvhDepth;
 	c->stats.scene_bytes = uint32_t(nodeBytes + primBytes + cs.mats.size() * sizeof(Mat));
 	return PT_OK;
+}
+
+int pt_set_scene(pt_context *c, size_t count, const pt_object_desc *objects)
+{
+	PT_TRY
+	if (!c) return setError(PT_E_INVALID, "pt_set_scene: null context");
+	if (count == 0)
+	{
+		printf("Setting an empty scene is not allowed!\n"); // Pathtracer.cpp:115
+		return PT_OK;
+	}
+	if (!objects) return setError(PT_E_INVALID, "pt_set_scene: null objects");
+	CompiledScene cs;
+	std::string err;
+	if (!compileScene(count, objects, c->maxLeaf, cs, err, c->maxGlobal)) return setError(PT_E_LIMIT, "pt_set_scene: " + err);
+	// the BVH is built ONCE on the host; a multi-GPU context replicates the compiled scene on every device
+	int r = uploadScene(c, cs);
+	for (size_t i = 0; r == PT_OK && i < c->peers.size(); ++i) r = uploadScene(c->peers[i], cs);
+	return r;
 	PT_CATCH(PT_E_LIMIT)
 }
 
@@ -226,7 +334,7 @@ static int uploadTextureTable(pt_context *c)
 	return PT_OK;
 }
 
-uint32_t pt_load_texture_mem(pt_context *c, uint32_t width, uint32_t height, int is_hdr, const void *rgba)
+static uint32_t loadTextureMemOne(pt_context *c, uint32_t width, uint32_t height, int is_hdr, const void *rgba)
 {
 	PT_TRY
 	if (!c || !rgba || width == 0 || height == 0) return 0;
@@ -290,6 +398,15 @@ uint32_t pt_load_texture_mem(pt_context *c, uint32_t width, uint32_t height, int
 	PT_CATCH(0u)
 }
 
+uint32_t pt_load_texture_mem(pt_context *c, uint32_t width, uint32_t height, int is_hdr, const void *rgba)
+{
+	const uint32_t h = loadTextureMemOne(c, width, height, is_hdr, rgba);
+	if (h != 0 && c)
+		for (pt_context *peer : c->peers)
+			if (loadTextureMemOne(peer, width, height, is_hdr, rgba) != h) { setError(PT_E_CUDA, "pt_load_texture: the devices of a multi-GPU context disagree on the texture handle"); return 0; }
+	return h;
+}
+
 uint32_t pt_load_texture(pt_context *c, const char *path)
 {
 	PT_TRY
@@ -306,6 +423,7 @@ int pt_set_skybox(pt_context *c, uint32_t handle)
 {
 	if (!c) return setError(PT_E_INVALID, "pt_set_skybox: null context");
 	c->skybox = handle;
+	for (pt_context *peer : c->peers) peer->skybox = handle;
 	return PT_OK;
 }
 
@@ -324,7 +442,7 @@ static SceneDev sceneDev(const pt_context *c)
 	return s;
 }
 
-int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ignore_history)
+static int renderOne(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ignore_history)
 {
 	PT_TRY
 	if (!c || !camera) return setError(PT_E_INVALID, "pt_render: bad arguments");
@@ -358,15 +476,16 @@ int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ign
 		p.seedHi = uint32_t(c->seed >> 32);
 		p.maxBounces = c->maxBounces;
 		p.regenLow = c->launch.regenLow > 0 ? uint32_t(c->launch.regenLow) : (c->launch.variant == 8 || c->launch.variant == 9 || c->launch.variant == 10 ? 8u : 16u);
-		// first-bounce stratification (RenderParams::strataPer): 2^k cells, k <= 7, at least 32 samples per cell - a pass of the
-		// one-pixel-per-warp kernel then holds samples of one cell
+		// first-bounce stratification (RenderParams::strataPer): 2^k cells, k <= 8, at least 16 samples per cell - the lanes of a
+		// pass of the one-pixel-per-warp kernel then hold samples of one or two neighbouring cells
 		const int v = c->launch.variant;
 		const bool perWarpKernel = v == 0 ? spp >= 64u : (v == 8 || v == 9 || v == 10 || v == 12 || v == 13); // launchTrace's choice
 		const bool wantStrata = perWarpKernel && (c->launch.stratify < 0 ? spp >= 128u : c->launch.stratify != 0) && spp >= 4u && spp < (1u << 21);
 		if (wantStrata)
 		{
 			uint32_t k = 2;
-			while (k < 7u && (spp >> (k + 1u)) >= 32u) ++k;
+			while (k < 8u && (spp >> (k + 1u)) >= 16u) ++k; // measured at 4096 spp: 32 / 64 / 128 / 256 / 512 cells -> 489 / 479 / 470 / 465 / 468 ms
+			if (c->launch.strataK > 0) k = uint32_t(c->launch.strataK); // (experiments: another cell count than the rule's)
 			while (k > 2u && (spp >> k) == 0u) --k;
 			p.strataBitsA = (k + 1u) / 2u;
 			p.strataBitsB = k / 2u;
@@ -405,13 +524,14 @@ int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ign
 			p.sortBitsB = b;
 		}
 		p.beam = c->launch.beam < 0 ? (spp >= 128u ? 1u : 0u) : uint32_t(c->launch.beam != 0);
+		p.alpha = c->alpha;
 		p.noJitter = c->noJitter ? 1u : 0u;
 		p.firstHitIndex = c->firstHit ? c->firstHitIndex : nullptr;
 		p.firstHitT = c->firstHit ? c->firstHitT : nullptr;
 		c->launch.stackLevels = int(c->bvhDepth) + 2;
 		CK(cudaEventRecord(c->evStart, c->stream)); // (all allocations are behind us: the events bracket the device work alone)
 		// pixel partition: the pixels of the other ranks hold zeros, so that the sum over ranks is the image
-		if (ignore_history && c->pixelStride > 1u) CK(cudaMemsetAsync(c->accum, 0, size_t(c->width) * c->height * sizeof(float4), c->stream));
+		if (ignore_history && c->pixelStride > 1u && !c->skipPartitionClear) CK(cudaMemsetAsync(c->accum, 0, size_t(c->width) * c->height * sizeof(float4), c->stream));
 		launches = launchTrace(p, c->launch, c->stream, &usedSmem);
 		if (launches < 0) return setError(PT_E_CUDA, std::string("pt_render: kernel launch failed: ") + cudaGetErrorString(cudaGetLastError()));
 	}
@@ -448,13 +568,173 @@ int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ign
 	PT_CATCH(PT_E_LIMIT)
 }
 
+static int loadNccl(pt_context *c)
+{
+	if (c->nccl) return PT_OK;
+	NcclState *n = new NcclState();
+	c->nccl = n;
+	const char *names[] = { "libnccl.so.2", "libnccl.so" };
+	for (const char *name : names)
+		if (!n->lib) n->lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+	if (!n->lib) return setError(PT_E_CUDA, std::string("multi-GPU: cannot load NCCL (libnccl.so.2): ") + dlerror());
+#define PT_SYM(field, sym) n->field = reinterpret_cast<decltype(n->field)>(dlsym(n->lib, sym)); if (!n->field) return setError(PT_E_CUDA, std::string("multi-GPU: NCCL lacks ") + sym)
+	PT_SYM(commInitAll, "ncclCommInitAll");
+	PT_SYM(commDestroy, "ncclCommDestroy");
+	PT_SYM(groupStart, "ncclGroupStart");
+	PT_SYM(groupEnd, "ncclGroupEnd");
+	PT_SYM(reduce, "ncclReduce");
+	PT_SYM(getErrorString, "ncclGetErrorString");
+#undef PT_SYM
+	std::vector<int> devs = { c->device };
+	for (pt_context *peer : c->peers) devs.push_back(peer->device);
+	n->comms.assign(devs.size(), nullptr);
+	const ncclResult_t r = n->commInitAll(n->comms.data(), int(devs.size()), devs.data());
+	if (r != ncclSuccess) return setError(PT_E_CUDA, std::string("multi-GPU: ncclCommInitAll failed: ") + n->getErrorString(r));
+	CK(cudaSetDevice(c->device));
+	CK(cudaEventCreate(&n->ev0));
+	CK(cudaEventCreate(&n->ev1));
+	return PT_OK;
+}
+
+// pt_render on a multi-GPU context: the work is split over the devices (option "partition"), every device renders its share
+// on its own host thread, and the image comes together on the root either by itself - pixel partition with peer access: the
+// kernels of the other devices store their pixels straight into the root's accumulation buffer over NVLink, 16 bytes per
+// pixel, no collective at all - or by ONE ncclReduce of the float4 accumulation buffers (option "exchange").
+static int renderMulti(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ignore_history)
+{
+	std::vector<pt_context *> all = { c };
+	all.insert(all.end(), c->peers.begin(), c->peers.end());
+	const uint32_t N = uint32_t(all.size());
+	const size_t px = size_t(c->width) * c->height;
+	const bool pixels = c->partition == 0;
+	const bool p2p = pixels && c->p2pReady && c->exchange != 0;
+	std::vector<uint32_t> share(N, spp);
+	for (uint32_t i = 0; i < N; ++i)
+	{
+		pt_context *d = all[i];
+		d->pixelOffset = pixels ? i : 0u;
+		d->pixelStride = pixels ? N : 1u;
+		d->sampleStride = pixels ? 1u : N;
+		const uint32_t off = pixels ? 0u : i;
+		if (d->sampleOffset != off) { d->sampleOffset = off; d->sampleCursor = off; } // (an unchanged offset must not rewind a progressive render)
+		if (!pixels) share[i] = spp > i ? (spp - i + N - 1u) / N : 0u;
+		d->skipPartitionClear = p2p;
+		d->alpha = (pixels || i == 0u) ? 1.0f : 0.0f; // sample partition: the summed alpha is 1, as on one GPU
+		if (i > 0)
+		{
+			// p2p: the peer renders into the ROOT's buffer; NCCL: into its own
+			float4 *want = p2p ? c->accum : nullptr;
+			if (want && d->accum != want)
+			{
+				CK(cudaSetDevice(d->device));
+				if (d->ownAccum && d->accum) CK(cudaFree(d->accum));
+				d->accum = want;
+				d->ownAccum = false;
+			}
+			else if (!want && !d->ownAccum)
+			{
+				CK(cudaSetDevice(d->device));
+				d->accum = nullptr;
+				CK(cudaMalloc(&d->accum, px * sizeof(float4)));
+				CK(cudaMemset(d->accum, 0, px * sizeof(float4)));
+				d->ownAccum = true;
+			}
+		}
+	}
+	if (!p2p && loadNccl(c) != PT_OK) return PT_E_CUDA;
+	// a device whose share of a restarting call is empty (sample partition, spp < devices) must not leave old sums in the reduce
+	for (uint32_t i = 0; i < N; ++i)
+		if (!p2p && ignore_history && share[i] == 0u)
+		{
+			CK(cudaSetDevice(all[i]->device));
+			CK(cudaMemsetAsync(all[i]->accum, 0, px * sizeof(float4), all[i]->stream));
+		}
+	// one host thread per GPU
+	std::vector<int> rc(N, PT_OK);
+	std::vector<std::string> errs(N);
+	std::vector<std::thread> threads;
+	for (uint32_t i = 1; i < N; ++i)
+		threads.emplace_back([&, i]() { rc[i] = renderOne(all[i], camera, share[i], ignore_history); if (rc[i] != PT_OK) errs[i] = g_lastError; });
+	rc[0] = renderOne(c, camera, share[0], ignore_history);
+	if (rc[0] != PT_OK) errs[0] = g_lastError;
+	for (std::thread &t : threads) t.join();
+	for (uint32_t i = 0; i < N; ++i)
+		if (rc[i] != PT_OK) return setError(rc[i], "device " + std::to_string(all[i]->device) + ": " + errs[i]);
+	float traceMs = 0.0f;
+	for (pt_context *d : all) traceMs = fmaxf(traceMs, d->timingMs);
+	c->reduceMs = 0.0f;
+	c->imageSource = nullptr;
+	if (!p2p)
+	{
+		NcclState *n = c->nccl;
+		CK(cudaSetDevice(c->device));
+		if (!c->reduced) CK(cudaMalloc(&c->reduced, px * sizeof(float4)));
+		ncclResult_t r = ncclSuccess;
+		// the communicators' first collective sets up the NVLink connections (~150 ms): done once, by an untimed reduce of the same
+		// buffers (into the same destination - the timed one below just repeats it), so that exchange_ms is the transfer
+		for (int pass = n->warm ? 1 : 0; pass < 2 && r == ncclSuccess; ++pass)
+		{
+			if (pass == 1) CK(cudaEventRecord(n->ev0, c->stream));
+			r = n->groupStart();
+			for (uint32_t i = 0; r == ncclSuccess && i < N; ++i)
+				r = n->reduce(all[i]->accum, c->reduced, px * 4, ncclFloat, ncclSum, 0, n->comms[i], all[i]->stream);
+			const ncclResult_t r2 = n->groupEnd();
+			if (r == ncclSuccess) r = r2;
+			if (pass == 0)
+				for (pt_context *d : all)
+				{
+					CK(cudaSetDevice(d->device));
+					CK(cudaStreamSynchronize(d->stream));
+				}
+			CK(cudaSetDevice(c->device));
+		}
+		n->warm = true;
+		if (r != ncclSuccess) return setError(PT_E_CUDA, std::string("multi-GPU: ncclReduce failed: ") + n->getErrorString(r));
+		CK(cudaSetDevice(c->device));
+		CK(cudaEventRecord(n->ev1, c->stream));
+		for (pt_context *d : all)
+		{
+			CK(cudaSetDevice(d->device));
+			CK(cudaStreamSynchronize(d->stream));
+		}
+		CK(cudaSetDevice(c->device));
+		CK(cudaEventElapsedTime(&c->reduceMs, n->ev0, n->ev1));
+		c->imageSource = c->reduced;
+	}
+	// the root answers for the whole job: timing (slowest device + exchange), counts for the normalisation, summed statistics
+	c->multiTraceMs = traceMs;
+	c->timingMs = traceMs + c->reduceMs;
+	if (ignore_history) { c->jobSamples = 0; c->jobFrames = 0; }
+	c->jobSamples += spp;
+	c->jobFrames += (c->framesPerSpp > 0) ? (spp + c->framesPerSpp - 1) / c->framesPerSpp : 1u;
+	c->totalSamples = c->jobSamples;
+	c->accumulatedFrames = c->jobFrames;
+	pt_stats sum = c->stats;
+	for (uint32_t i = 1; i < N; ++i)
+	{
+		const pt_stats &s = all[i]->stats;
+		sum.samples += s.samples; sum.rays += s.rays; sum.node_visits += s.node_visits; sum.prim_tests += s.prim_tests; sum.shades += s.shades; sum.misses += s.misses;
+	}
+	sum.gpu_ms = c->timingMs;
+	c->multiStats = sum;
+	return PT_OK;
+}
+
+int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ignore_history)
+{
+	PT_TRY
+	if (!c || !camera) return setError(PT_E_INVALID, "pt_render: bad arguments");
+	return c->peers.empty() ? renderOne(c, camera, spp, ignore_history) : renderMulti(c, camera, spp, ignore_history);
+	PT_CATCH(PT_E_LIMIT)
+}
+
 float pt_get_timing_ms(const pt_context *c) { return c ? c->timingMs : 0.0f; }
 
 static const float *readHdr(pt_context *c, float scale)
 {
 	if (cudaSetDevice(c->device) != cudaSuccess) return nullptr;
 	const uint32_t px = c->width * c->height;
-	launchScale(c->accum, c->scaledDev, px, scale, c->stream);
+	launchScale(c->imageSource ? c->imageSource : c->accum, c->scaledDev, px, scale, c->stream);
 	if (cudaMemcpyAsync(c->hostHdr, c->scaledDev, size_t(px) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
 	    cudaStreamSynchronize(c->stream) != cudaSuccess)
 	{
@@ -489,7 +769,7 @@ const uint8_t *pt_get_ldr(pt_context *c)
 	const uint32_t px = c->width * c->height;
 	// tonemap.cu:17 divides by float(accumulatedSampleCount) via reciprocal-multiply; 0 frames -> division by zero in the
 	// reference; here the accumulation is zero in that case and the scale is clamped like getHDRImageData's
-	launchTonemap(c->accum, c->ldrDev, px, 1.0f / fmaxf(float(c->accumulatedFrames), 1.0f), c->stream);
+	launchTonemap(c->imageSource ? c->imageSource : c->accum, c->ldrDev, px, 1.0f / fmaxf(float(c->accumulatedFrames), 1.0f), c->stream);
 	if (cudaMemcpyAsync(c->hostLdr, c->ldrDev, size_t(px) * sizeof(uchar4), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
 	    cudaStreamSynchronize(c->stream) != cudaSuccess)
 	{
@@ -499,7 +779,7 @@ const uint8_t *pt_get_ldr(pt_context *c)
 	return c->hostLdr;
 }
 
-int pt_set_option(pt_context *c, const char *key, double value)
+static int setOptionOne(pt_context *c, const char *key, double value)
 {
 	PT_TRY
 	if (!c || !key) return setError(PT_E_INVALID, "pt_set_option: bad arguments");
@@ -528,7 +808,9 @@ int pt_set_option(pt_context *c, const char *key, double value)
 	else if (k == "regen_low") c->launch.regenLow = int(value);
 	else if (k == "beam") c->launch.beam = int(value);
 	else if (k == "sort_samples") c->launch.sortSamples = int(value);
+	else if (k == "alpha") c->alpha = float(value);
 	else if (k == "stratify") c->launch.stratify = int(value);
+	else if (k == "strata_k") c->launch.strataK = value < 2 ? 0 : (value > 10 ? 10 : int(value));
 	else if (k == "smem_stack") c->launch.smemStack = int(value);
 	else if (k == "jitter") c->noJitter = value == 0;
 	else if (k == "first_hit")
@@ -552,6 +834,19 @@ int pt_set_option(pt_context *c, const char *key, double value)
 	PT_CATCH(PT_E_LIMIT)
 }
 
+int pt_set_option(pt_context *c, const char *key, double value)
+{
+	if (!c || !key) return setError(PT_E_INVALID, "pt_set_option: bad arguments");
+	const std::string k(key);
+	if (k == "partition") { c->partition = value != 0 ? 1 : 0; return PT_OK; }
+	if (k == "exchange") { c->exchange = value < 0 ? -1 : (value != 0 ? 1 : 0); return PT_OK; }
+	if (!c->peers.empty() && (k == "pixel_offset" || k == "pixel_stride" || k == "sample_offset" || k == "sample_stride"))
+		return setError(PT_E_INVALID, "pt_set_option: a multi-GPU context sets the partition options of its devices itself (use \"partition\")");
+	int r = setOptionOne(c, key, value);
+	for (size_t i = 0; r == PT_OK && i < c->peers.size(); ++i) r = setOptionOne(c->peers[i], key, value);
+	return r;
+}
+
 /* debugging aid (not in the header): raw device counters of the last pt_render, see trace_kernels.h kCtr* */
 extern "C" int pt_debug_counters(const pt_context *c, unsigned long long *out, int n)
 {
@@ -564,7 +859,7 @@ extern "C" int pt_debug_counters(const pt_context *c, unsigned long long *out, i
 int pt_get_stats(const pt_context *c, pt_stats *out)
 {
 	if (!c || !out) return setError(PT_E_INVALID, "pt_get_stats: bad arguments");
-	*out = c->stats;
+	*out = c->peers.empty() ? c->stats : c->multiStats;
 	return PT_OK;
 }
 
@@ -637,6 +932,7 @@ void *pt_accum_device_ptr(pt_context *c) { return c ? (void *)c->accum : nullptr
 int pt_set_accum_device_ptr(pt_context *c, void *device_ptr)
 {
 	if (!c || !device_ptr) return setError(PT_E_INVALID, "pt_set_accum_device_ptr: bad arguments");
+	if (!c->peers.empty()) return setError(PT_E_INVALID, "pt_set_accum_device_ptr: not on a multi-GPU context (it owns the exchange)");
 	CK(cudaSetDevice(c->device));
 	CK(cudaStreamSynchronize(c->stream));
 	if (c->ownAccum && c->accum) CK(cudaFree(c->accum));

@@ -11,7 +11,11 @@ constexpr int kThreads = 256;
 // the trace kernel runs one CTA of 32 warps per SM: 64 registers per thread (no spills), ONE shared-memory copy of the
 // scene per SM, the rest of the 228 KB stays L1 for the traversal stack / materials / textures (measured on
 // generated_scene: 3 x 256 threads 12.3, 2 x 512 12.9, 1 x 1024 13.2 Grays/s)
-constexpr int kTraceThreads = 1024;
+#ifndef PTB_TRACE_THREADS
+#define PTB_TRACE_THREADS 1024
+#endif
+constexpr int kTraceThreads = PTB_TRACE_THREADS;
+static_assert(kTraceThreads % 32 == 0 && kTraceThreads * 4 <= int(kStackStride), "the shared-memory stack holds one int per thread and level");
 
 // pixel index -> (x, y) without an integer division (exact while the index is exact in fp32; one correction step)
 __device__ __forceinline__ void pixelToXY(uint32_t pixel, uint32_t width, uint32_t height, uint32_t &px, uint32_t &py)

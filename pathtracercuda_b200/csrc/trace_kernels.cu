@@ -139,14 +139,18 @@ template <bool SMEM, bool COUNT, int TRAV, bool SHARE, bool SPLIT = false, bool 
 __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_constant__ RenderParams p)
 {
 	extern __shared__ __align__(128) float4 smemScene[];
+	// shared-window address of the dynamic shared memory, made opaque to the compiler: left alone it RE-DERIVES the address at
+	// every use (S2UR SR_CgaCtaId, UMOV, UIADD3, ULEA ... five issue slots per primitive test) instead of keeping one register
+	uint32_t smemBase = uint32_t(__cvta_generic_to_shared(smemScene));
+	asm volatile("" : "+r"(smemBase));
 	// SSTACK: this thread's column of the shared-memory traversal stack (trace_device.cuh TravStack<true>), behind the scene copy
-	const uint32_t stackColumn = SSTACK ? uint32_t(__cvta_generic_to_shared(smemScene)) + p.stackOffset + threadIdx.x * 4u : 0u;
+	const uint32_t stackColumn = SSTACK ? smemBase + p.stackOffset + threadIdx.x * 4u : 0u;
 	__shared__ uint64_t mbar;
 	SceneView<SMEM> sv;
 	if constexpr (SMEM)
 	{
 		stageSceneToSmem(smemScene, p.scene.sceneBlob, (p.scene.nodeCount + p.scene.primCount) * 64u, &mbar);
-		sv.nodes = smemWindow(smemScene);
+		sv.nodes = reinterpret_cast<const float4 *>(uintptr_t(smemBase));
 		sv.prims = sv.nodes + size_t(p.scene.nodeCount) * 4;
 		sv.globalCount = p.scene.globalCount;
 	}
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 						}
 						if (lane == 0)
 						{
-							float4 out = make_float4(color.x, color.y, color.z, 1.0f); // trace.cu:196-198
+							float4 out = make_float4(color.x, color.y, color.z, p.alpha); // trace.cu:196-198
 							if (!p.ignoreHistory)
 							{
 								const float4 prev = p.accum[pixel];
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 		const bool need = active && !alive && sample == p.spp;
 		if (need && pixel != kInvalid)
 		{
-			float4 out = make_float4(color.x, color.y, color.z, 1.0f); // trace.cu:196-198
+			float4 out = make_float4(color.x, color.y, color.z, p.alpha); // trace.cu:196-198
 			if (!p.ignoreHistory)
 			{
 				const float4 prev = p.accum[pixel];
@@ -353,7 +357,10 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 					}
 				}
 				ro = camO;
-				rd = cameraDir<kHotExact>(p.cam, u, v);
+				// IEEE square root and division here, as in the reference's Camera::getRay: far from an object the quadratic of the
+				// primitive test cancels ~7 digits, so a direction that differs in its last bit re-rolls which silhouette pixels
+				// hit - with the exact direction (and toLocalOD's rounding order) the render kernel's first hits are the reference's
+				rd = cameraDir<true>(p.cam, u, v);
 				thr = mk(1.0f, 1.0f, 1.0f);
 				L = mk(0.0f, 0.0f, 0.0f);
 				bounce = 0;
@@ -396,38 +403,44 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 			else
 			{
 				// ---- shade / sample (trace.cu:136-151) ----
-				if (COUNT) ++shades;
-				const Surface s = surfaceAt<SMEM>(sv, h.prim, ro, rd, h.t);
 				const float4 *mp = reinterpret_cast<const float4 *>(p.scene.mats + h.prim);
-				const float4 m0 = __ldg(mp), m1 = __ldg(mp + 1), m2 = __ldg(mp + 2);
+				const float4 m1 = __ldg(mp + 1);
 				if constexpr (SHARE) color = color + thr * mk(m1.x, m1.y, m1.z); // getEmitted, Material.inl:62-65
 				else L = L + thr * mk(m1.x, m1.y, m1.z);
-				V3 base = mk(m0.x, m0.y, m0.z);
-				const uint32_t tex = __float_as_uint(m2.x), mtype = __float_as_uint(m2.y);
-				if (tex != 0 && tex <= p.scene.texCount)
+				terminate = true;
+				// The last segment of a path only contributes what it hits: the direction the reference still samples there
+				// (trace.cu:139-151 in its fifth loop trip) is never traced and its weight never reaches the image - no normal,
+				// texture tap or BSDF sample for it.
+				if (bounce + 1u < p.maxBounces)
 				{
-					const V3 tap = texLookupNI(p.scene.textures, tex, s.u, s.v); // Material.inl:26-35
-					base = mk(fastPow(tap.x, 2.2f), fastPow(tap.y, 2.2f), fastPow(tap.z, 2.2f));
-				}
-				float rnd0, rnd1;
-				if (bounce == 0) { rnd0 = uniform01(rz); rnd1 = uniform01(rw); }
-				else if (bounce & 1u)
-				{
-					const uint4 r = philoxNI(pixel, sampleIdx, (bounce + 1u) >> 1, p.seedLo, p.seedHi);
-					rnd0 = uniform01(r.x); rnd1 = uniform01(r.y);
-					rz = r.z; rw = r.w;
-				}
-				else { rnd0 = uniform01(rz); rnd1 = uniform01(rw); }
-				V3 wi, weight;
-				const bool cont = sampleMaterial(mtype, base, m0.w, m1.w, s.n, rd, rnd0, rnd1, wi, weight);
-				terminate = !cont;
-				if (cont)
-				{
-					thr = thr * weight;
-					ro = s.p;
-					rd = wi;
-					++bounce;
-					if (bounce >= p.maxBounces) terminate = true;
+					if (COUNT) ++shades;
+					const Surface s = surfaceAt<SMEM>(sv, h.prim, ro, rd, h.t);
+					const float4 m0 = __ldg(mp), m2 = __ldg(mp + 2);
+					V3 base = mk(m0.x, m0.y, m0.z);
+					const uint32_t tex = __float_as_uint(m2.x), mtype = __float_as_uint(m2.y);
+					if (tex != 0 && tex <= p.scene.texCount)
+					{
+						const V3 tap = texLookupNI(p.scene.textures, tex, s.u, s.v); // Material.inl:26-35
+						base = mk(fastPow(tap.x, 2.2f), fastPow(tap.y, 2.2f), fastPow(tap.z, 2.2f));
+					}
+					float rnd0, rnd1;
+					if (bounce == 0) { rnd0 = uniform01(rz); rnd1 = uniform01(rw); }
+					else if (bounce & 1u)
+					{
+						const uint4 r = philoxNI(pixel, sampleIdx, (bounce + 1u) >> 1, p.seedLo, p.seedHi);
+						rnd0 = uniform01(r.x); rnd1 = uniform01(r.y);
+						rz = r.z; rw = r.w;
+					}
+					else { rnd0 = uniform01(rz); rnd1 = uniform01(rw); }
+					V3 wi, weight;
+					if (sampleMaterial(mtype, base, m0.w, m1.w, s.n, rd, rnd0, rnd1, wi, weight))
+					{
+						thr = thr * weight;
+						ro = s.p;
+						rd = wi;
+						++bounce;
+						terminate = false;
+					}
 				}
 			}
 			if (terminate)

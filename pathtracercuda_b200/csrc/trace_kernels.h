@@ -52,6 +52,8 @@ struct RenderParams
 	uint32_t noJitter = 0;          // parity aid: every sample through the pixel centre (u = (x + 0.5) / W, like the reference's primary pass)
 	int32_t *firstHitIndex = nullptr; // parity aid: scene index (-1: miss) and t of the camera ray's closest hit, per pixel, written by
 	float *firstHitT = nullptr;       // the render kernel itself (with noJitter every sample of a pixel writes the same values)
+	float alpha = 1.0f;             // what the kernel writes to the accumulation buffer's fourth channel (trace.cu:198 writes 1); a multi-GPU
+	                                // sample partition lets only its first device write 1, so that the summed alpha is 1 as on one GPU
 	uint32_t stackOffset = 0;       // SSTACK kernels: byte offset of the shared-memory traversal stack in dynamic shared memory
 };
 
@@ -68,6 +70,7 @@ struct LaunchConfig
 	int sortSamples = 0; // order a pixel's samples by first scattering direction (round 1; superseded by `stratify`): 1 on, 0 off (default)
 	int beam = -1;       // pixel beams for the camera rays of the one-pixel-per-warp kernel: 1 on, 0 off, -1 = on from 128 spp
 	int stratify = -1;   // first-bounce stratification (RenderParams::strataPer): 1 on, 0 off, -1 = on from 128 spp (one-pixel-per-warp kernels)
+	int strataK = 0;     // experiments: log2 of the cell count (0 = the rule of pt_render: at least 32 samples per cell, at most 128 cells)
 	int smemStack = -1;  // traversal stack in shared memory (TravStack<true>): 1 on, 0 off, -1 = on when it fits beside the scene
 	int stackLevels = 0; // BVH depth + 2: levels the shared-memory stack needs (set by pt_render from the compiled scene)
 	size_t maxSmemOptin = 0;

@@ -41,6 +41,7 @@ def configure_partition(tracer, spp, rank, world, partition="pixels"):
         tracer.setOption("sample_offset", 0)
         tracer.setOption("pixel_stride", stride)
         tracer.setOption("pixel_offset", off)
+        tracer.setOption("alpha", 1.0)
         return spp
     if partition != "samples":
         raise ValueError("partition must be 'pixels' or 'samples'")
@@ -49,6 +50,7 @@ def configure_partition(tracer, spp, rank, world, partition="pixels"):
     tracer.setOption("pixel_offset", 0)
     tracer.setOption("sample_stride", stride)
     tracer.setOption("sample_offset", off)
+    tracer.setOption("alpha", 1.0 if rank == 0 else 0.0)  # every rank writes every pixel: only one of them the alpha of 1 (trace.cu:198)
     return count
 
 

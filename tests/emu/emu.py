@@ -68,6 +68,14 @@ class Emu:
         self.L.emu_fast_angles(y.size, _p(y), _p(x), _p(a), _p(c))
         return a, c
 
+    def first_hit(self, cam, w, h, beam=True):
+        """the production kernel's first-hit path (pixel beam + closestHitWW, hot-path arithmetic) for pixel-centre rays"""
+        idx = np.zeros(w * h, np.int32)
+        t = np.zeros(w * h, np.float32)
+        self.L.emu_first_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p]
+        self.L.emu_first_hit(self.s, C.byref(cam), w, h, int(beam), _p(idx), _p(t))
+        return idx, t
+
     def global_count(self):
         self.L.emu_global_count.restype = C.c_uint32
         self.L.emu_global_count.argtypes = [C.c_void_p]

@@ -128,6 +128,36 @@ void emu_primary(void *p, const pt_camera_desc *cd, uint32_t width, uint32_t hei
 	if (stats2) { stats2[0] = nvTot; stats2[1] = ptTot; }
 }
 
+// mirrors what the production kernel does for the camera ray of a pixel with option jitter = 0: the pixel's beam list
+// (beamLeaves), then closestHitWW with the hot-path arithmetic - the first-hit gate of tests/test_gpu_baseline_sizes.py on the CPU
+void emu_first_hit(void *p, const pt_camera_desc *cd, uint32_t width, uint32_t height, int useBeam, int32_t *hitIndex, float *hitT)
+{
+	EmuScene *s = (EmuScene *)p;
+	CameraDev cam;
+	computeCamera(*cd, cam);
+	const SceneView<false> sv = s->view();
+	const float invW = 1.0f / float(width), invH = 1.0f / float(height);
+#pragma omp parallel for schedule(dynamic, 4)
+	for (int y = 0; y < (int)height; ++y)
+		for (uint32_t x = 0; x < width; ++x)
+		{
+			const uint32_t i = x + uint32_t(y) * width;
+			uint32_t nv = 0, pt = 0;
+			BeamEntry beam[kBeamMax];
+			int nBeam = -1;
+			const float m = 1.0f / 64.0f;
+			if (useBeam)
+				nBeam = beamLeaves<false>(sv.nodes, s->cs.treeNodeCount, uint32_t(s->cs.nodes.size()), cam, (float(x) - m) * invW, (float(x) + 1.0f + m) * invW, (float(y) - m) * invH,
+				                          (float(y) + 1.0f + m) * invH, beam, true);
+			const float u = (float(x) + 0.5f) / float(width), v = (float(y) + 0.5f) / float(height);
+			const V3 o = mk(cam.origin[0], cam.origin[1], cam.origin[2]);
+			const V3 d = cameraDir<kHotExact>(cam, u, v);
+			const Hit h = closestHitWW<false, true, false, kHotExact>(sv, o, d, 0.001f, nv, pt, beam, nBeam);
+			hitIndex[i] = h.prim < 0 ? -1 : int32_t(__float_as_uint(sv.prims[h.prim * 4 + 3].y));
+			hitT[i] = h.prim < 0 ? 0.0f : h.t;
+		}
+}
+
 // mirrors traceRaysKernel
 void emu_trace_rays(void *p, size_t n, const float *origins, const float *directions, float tMin, int32_t *hitIndex, float *hitT, float *hitNormal)
 {

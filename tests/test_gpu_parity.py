@@ -126,7 +126,10 @@ def test_render_matches_oracle_path_for_path(scene, W, H, spp):
         st = P.stats()
     assert abs(int(st.rays) - int(ra)) <= 5e-4 * ra and st.samples == W * H * spp
     rel = np.abs(a - b)[..., :3] / (np.abs(a[..., :3]) + 1e-3 * spp)
-    assert (rel.max(-1) > 1e-3).mean() < 0.04
+    # a path that parts ways (a last-bit difference decides a hit or a lobe) moves its pixel's sum by ~1/spp of it: the more
+    # samples a pixel has, the more of its paths do - so the per-pixel tolerance grows with spp, the share of pixels allowed
+    # beyond it does not
+    assert (rel.max(-1) > 1e-3 * max(1.0, spp / 64)).mean() < 0.04
     assert abs(a[..., :3].mean() / b[..., :3].mean() - 1) < 2e-3
     assert imgio.rmse(a / spp, b / spp)[0] < 0.02
 
@@ -466,3 +469,51 @@ def test_large_synthetic_scene_global_memory_path():
     # scenes the reference's own GPU code traces 0.1-0.7 % fewer rays than its host build (measured) and so do we
     assert -1e-2 * ra < int(st.rays) - int(ra) < 2e-3 * ra
     assert np.isfinite(img).all()
+
+
+def test_multi_gpu_context_through_the_c_abi(tmp_path):
+    """pt_create_multi (two GPUs of one box, one host thread each inside pt_render): the same entry points as a single-device
+    context.  Pixel partition - by peer-to-peer stores into the root's buffer and by one ncclReduce - is bit-identical to one
+    GPU; the sample partition (north_star's split, always ncclReduce) agrees up to summation order; progressive calls keep
+    accumulating; the getters normalise by the whole job's counts; the CLI's --gpus renders the same PNG."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    W, H, spp = 200, 120, 96
+    scene = f"{pt.ASSETS}/scenes/generated_scene.json"
+
+    def run(mask, partition=0, exchange=-1, stratify=-1):
+        with pt.Pathtracer(W, H, device_mask=mask) as P:
+            cam = P.loadSceneFile(scene, cwd=pt.ASSETS)
+            if mask:
+                P.setOption("partition", partition)
+                P.setOption("exchange", exchange)
+            P.setOption("stratify", stratify)
+            P.render(cam, spp, True)
+            first, st1, info = P.getHDRMean().copy(), P.stats(), P.multiInfo()
+            P.render(cam, 40, False)
+            both, frames = P.getHDRMean().copy(), P.getHDRImageData().copy()
+            return first, both, frames, st1, info, P.getImageData().copy()
+    one = run(0)
+    p2p = run(3, 0, -1)
+    red = run(3, 0, 0)
+    assert one[4][0] == 1 and p2p[4][0] == 2 and red[4][0] == 2
+    assert red[4][1] is False and red[4][3] > 0.0  # ncclReduce: its device time is reported on its own
+    if p2p[4][1]:
+        assert p2p[4][3] == 0.0                    # peer-to-peer stores: there is no exchange step
+    for m in (p2p, red):
+        assert np.array_equal(bits(m[0]), bits(one[0])) and np.array_equal(bits(m[1]), bits(one[1])) and np.array_equal(bits(m[2]), bits(one[2]))
+        assert np.array_equal(m[5], one[5]) and m[3].rays == one[3].rays and m[3].samples == one[3].samples == W * H * spp
+    # sample partition: each device stratifies its own launch, so compare with plain Philox draws (same sample set at any N)
+    one_plain, smp = run(0, stratify=0), run(3, 1, 0, stratify=0)
+    assert smp[4][1] is False
+    assert np.allclose(smp[0], one_plain[0], rtol=3e-5, atol=1e-6) and np.allclose(smp[1], one_plain[1], rtol=3e-5, atol=1e-6)
+    assert np.allclose(smp[2][..., :3], one_plain[2][..., :3], rtol=3e-5, atol=1e-6) and smp[3].rays == one_plain[3].rays
+    assert np.allclose(smp[1][..., 3], one_plain[1][..., 3]) and np.allclose(smp[2][..., 3], one_plain[2][..., 3])  # alpha as on one GPU (only the first device writes the 1 of trace.cu:198)
+    # the command line
+    a, b = str(tmp_path / "one.png"), str(tmp_path / "two.png")
+    for out, extra in ((a, []), (b, ["--gpus", "2", "--stats"])):
+        r = subprocess.run([CLI, "-w", str(W), "-h", str(H), "-spp", "64", "-o", out] + extra + ["scenes/generated_scene.json"], cwd=pt.ASSETS, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    assert '"devices": 2' in r.stdout
+    assert np.array_equal(imgio.read_png(a), imgio.read_png(b))

@@ -38,9 +38,9 @@ def test_pixel_partition_covers_every_pixel_once_and_sets_the_options():
         def setOption(self, k, v): self.opts[k] = v
     t = Stub()
     assert configure_partition(t, 4096, 3, 8, "pixels") == 4096
-    assert t.opts == {"sample_stride": 1, "sample_offset": 0, "pixel_stride": 8, "pixel_offset": 3}
+    assert t.opts == {"sample_stride": 1, "sample_offset": 0, "pixel_stride": 8, "pixel_offset": 3, "alpha": 1.0}
     assert configure_partition(t, 4096, 3, 8, "samples") == 512
-    assert t.opts == {"sample_stride": 8, "sample_offset": 3, "pixel_stride": 1, "pixel_offset": 0}
+    assert t.opts == {"sample_stride": 8, "sample_offset": 3, "pixel_stride": 1, "pixel_offset": 0, "alpha": 0.0}
     with pytest.raises(ValueError):
         configure_partition(t, 8, 0, 2, "tiles")
 
@@ -51,14 +51,14 @@ class _OracleTracer:
 
     def __init__(self, O, cam, W, H):
         self.O, self.cam, self.W, self.H = O, cam, W, H
-        self.opts = {"sample_offset": 0, "sample_stride": 1, "pixel_offset": 0, "pixel_stride": 1}
+        self.opts = {"sample_offset": 0, "sample_stride": 1, "pixel_offset": 0, "pixel_stride": 1, "alpha": 1}
         self.cursor = 0
         self.accum = torch.zeros((H, W, 4), dtype=torch.float32)
 
     def setOption(self, k, v):
         if k == "sample_offset" and int(v) != self.opts[k]:
             self.cursor = int(v)
-        self.opts[k] = int(v)
+        self.opts[k] = v if k == "alpha" else int(v)
 
     def render(self, cam, spp, ignore_history):
         if ignore_history:
