@@ -474,6 +474,7 @@ static int renderOne(pt_context *c, const pt_camera_desc *camera, uint32_t spp, 
 		p.pixelStride = c->pixelStride;
 		p.seedLo = uint32_t(c->seed);
 		p.seedHi = uint32_t(c->seed >> 32);
+		for (uint32_t i = 0; i < 10; ++i) { p.philoxKeys[2 * i] = p.seedLo + i * 0x9E3779B9u; p.philoxKeys[2 * i + 1] = p.seedHi + i * 0xBB67AE85u; }
 		p.maxBounces = c->maxBounces;
 		p.regenLow = c->launch.regenLow > 0 ? uint32_t(c->launch.regenLow) : (c->launch.variant == 8 || c->launch.variant == 9 || c->launch.variant == 10 ? 8u : 16u);
 		// first-bounce stratification (RenderParams::strataPer): 2^k cells, k <= 8, at least 16 samples per cell - the lanes of a

@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 
 	// SHARE: the leaves the camera rays of the warp's pixel can reach (beamLeaves), nearest first
 	__shared__ BeamEntry beamList[SHARE && TRAV >= 1 ? kTraceThreads / 32 : 1][kBeamMax];
+	__shared__ BeamBox beamBoxes[SHARE && TRAV >= 1 && !SMEM ? kTraceThreads / 32 : 1][kBeamMax]; // scenes in global memory: the leaves' boxes (trace_device.cuh BeamBox)
 	int nBeam = -1;
 	// SPLIT: per-warp bin counters of sortSamples, and the warp's slice of the sample-order scratch
 	__shared__ float2 pixelXY[SHARE ? kTraceThreads / 32 : 1]; // SHARE: (x, y) of the warp's pixel, once per pixel instead of once per sample
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 							pixelToXY(pixel, p.width, p.height, px, py);
 							const float m = 1.0f / 64.0f; // footprint widened: the jittered (s, t) are rounded products
 							nBeam = beamLeaves<SMEM>(sv.nodes, p.scene.treeNodeCount, p.scene.nodeCount, p.cam, (float(px) - m) * invW, (float(px) + 1.0f + m) * invW, (float(py) - m) * invH,
-							                         (float(py) + 1.0f + m) * invH, beamList[threadIdx.x >> 5], lane == 0);
+							                         (float(py) + 1.0f + m) * invH, beamList[threadIdx.x >> 5], lane == 0, SMEM ? nullptr : beamBoxes[threadIdx.x >> 5]);
 							__syncwarp();
 						}
 					}
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 			if (generate)
 			{
 				sampleIdx = p.sampleOffset + sample * p.sampleStride;
-				const uint4 r = philoxNI(pixel, sampleIdx, 0u, p.seedLo, p.seedHi);
+				const uint4 r = philox4x32_10_keyed(pixel, sampleIdx, 0u, 0u, p.philoxKeys);
 				float pxf, pyf;
 				if constexpr (SHARE) { const float2 xy = pixelXY[threadIdx.x >> 5]; pxf = xy.x; pyf = xy.y; }
 				else
@@ -371,9 +372,9 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 			++rays;
 			const Hit h = TRAV == 0 ? closestHit<SMEM, COUNT, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests)
 			              : TRAV == 1 ? closestHitWW<SMEM, COUNT, false, kHotExact, SSTACK>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? threadIdx.x >> 5 : 0],
-			                                                                                SHARE && bounce == 0 ? nBeam : -1, stackColumn)
+			                                                                                SHARE && bounce == 0 ? nBeam : -1, stackColumn, SMEM ? nullptr : beamBoxes[SHARE ? threadIdx.x >> 5 : 0])
 			                          : closestHitWW<SMEM, COUNT, true, kHotExact, SSTACK>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? threadIdx.x >> 5 : 0],
-			                                                                               SHARE && bounce == 0 ? nBeam : -1, stackColumn);
+			                                                                               SHARE && bounce == 0 ? nBeam : -1, stackColumn, SMEM ? nullptr : beamBoxes[SHARE ? threadIdx.x >> 5 : 0]);
 			if (bounce == 0 && p.firstHitIndex != nullptr)
 			{
 				// parity aid: what THIS kernel's traversal found for the camera ray (scene-order index, t), per pixel
@@ -427,7 +428,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 					if (bounce == 0) { rnd0 = uniform01(rz); rnd1 = uniform01(rw); }
 					else if (bounce & 1u)
 					{
-						const uint4 r = philoxNI(pixel, sampleIdx, (bounce + 1u) >> 1, p.seedLo, p.seedHi);
+						const uint4 r = philox4x32_10_keyed(pixel, sampleIdx, (bounce + 1u) >> 1, 0u, p.philoxKeys);
 						rnd0 = uniform01(r.x); rnd1 = uniform01(r.y);
 						rz = r.z; rw = r.w;
 					}
@@ -582,8 +583,9 @@ static int launchKernel(K kern, const RenderParams &p, const LaunchConfig &cfg, 
 	return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
 }
 
-// static shared memory of the trace kernels (beam lists, per-warp pixel coordinates, sort counters, barrier) - an upper bound
-constexpr size_t kStaticSmemBound = 24576;
+// static shared memory of the trace kernels (beam lists, per-warp pixel coordinates, sort counters, barrier; + the beam boxes of
+// the global-memory instantiations) - an upper bound; launchKernel has the last word (occupancy query)
+constexpr size_t kStaticSmemBound = 36864;
 
 int launchTrace(const RenderParams &pIn, const LaunchConfig &cfg, cudaStream_t stream, int *usedSmem)
 {

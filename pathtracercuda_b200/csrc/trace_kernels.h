@@ -32,6 +32,9 @@ struct RenderParams
 	uint32_t sampleOffset, sampleStride;
 	uint32_t pixelOffset = 0, pixelStride = 1; // this launch renders pixels offset, offset + stride, ... (multi-GPU pixel partition)
 	uint32_t seedLo, seedHi;
+	// the ten round keys of Philox4x32-10 (key + i * Weyl constants), worked out once on the host: in the kernel they are
+	// constant-bank operands of the rounds' XORs instead of two additions per round (a third of the generator's instructions)
+	uint32_t philoxKeys[20];
 	uint32_t maxBounces;
 	uint32_t regenLow = 1; // one-pixel-per-warp kernel: idle lanes wait until this many can start new samples together
 	// one-pixel-per-warp kernel: the samples of a pixel are handed out in the order of their first scattering direction

@@ -144,15 +144,16 @@ void emu_first_hit(void *p, const pt_camera_desc *cd, uint32_t width, uint32_t h
 			const uint32_t i = x + uint32_t(y) * width;
 			uint32_t nv = 0, pt = 0;
 			BeamEntry beam[kBeamMax];
+			BeamBox boxes[kBeamMax];
 			int nBeam = -1;
 			const float m = 1.0f / 64.0f;
 			if (useBeam)
 				nBeam = beamLeaves<false>(sv.nodes, s->cs.treeNodeCount, uint32_t(s->cs.nodes.size()), cam, (float(x) - m) * invW, (float(x) + 1.0f + m) * invW, (float(y) - m) * invH,
-				                          (float(y) + 1.0f + m) * invH, beam, true);
+				                          (float(y) + 1.0f + m) * invH, beam, true, boxes);
 			const float u = (float(x) + 0.5f) / float(width), v = (float(y) + 0.5f) / float(height);
 			const V3 o = mk(cam.origin[0], cam.origin[1], cam.origin[2]);
 			const V3 d = cameraDir<kHotExact>(cam, u, v);
-			const Hit h = closestHitWW<false, true, false, kHotExact>(sv, o, d, 0.001f, nv, pt, beam, nBeam);
+			const Hit h = closestHitWW<false, true, false, kHotExact>(sv, o, d, 0.001f, nv, pt, beam, nBeam, 0, boxes);
 			hitIndex[i] = h.prim < 0 ? -1 : int32_t(__float_as_uint(sv.prims[h.prim * 4 + 3].y));
 			hitT[i] = h.prim < 0 ? 0.0f : h.t;
 		}
@@ -200,11 +201,12 @@ uint64_t emu_render(void *p, const pt_camera_desc *cd, uint32_t width, uint32_t 
 			const uint32_t pixel = x + uint32_t(y) * width;
 			V3 color = mk(0.0f, 0.0f, 0.0f);
 			BeamEntry beam[kBeamMax];
+			BeamBox boxes[kBeamMax];
 			int nBeam = -1;
 			if (g_beam)
 			{
 				const float m = 1.0f / 64.0f;
-				nBeam = beamLeaves<false>(sv.nodes, s->cs.treeNodeCount, uint32_t(s->cs.nodes.size()), cam, (float(x) - m) * invW, (float(x) + 1.0f + m) * invW, (float(y) - m) * invH, (float(y) + 1.0f + m) * invH, beam, true);
+				nBeam = beamLeaves<false>(sv.nodes, s->cs.treeNodeCount, uint32_t(s->cs.nodes.size()), cam, (float(x) - m) * invW, (float(x) + 1.0f + m) * invW, (float(y) - m) * invH, (float(y) + 1.0f + m) * invH, beam, true, boxes);
 #pragma omp critical
 				{
 					++g_beamStats[0];
@@ -224,7 +226,7 @@ uint64_t emu_render(void *p, const pt_camera_desc *cd, uint32_t width, uint32_t 
 				{
 					++raysTot;
 					uint32_t nv = 0, pt = 0;
-					const Hit h = g_beam ? closestHitWW<false, true, false, kHotExact>(sv, ro, rd, 0.001f, nv, pt, beam, bounce == 0 ? nBeam : -1)
+					const Hit h = g_beam ? closestHitWW<false, true, false, kHotExact>(sv, ro, rd, 0.001f, nv, pt, beam, bounce == 0 ? nBeam : -1, 0, boxes)
 					                     : closestHit<false, true, kHotExact>(sv, ro, rd, 0.001f, nv, pt);
 					nvTot += nv; ptTot += pt;
 					if (h.prim < 0)
