@@ -857,6 +857,22 @@ extern "C" int pt_debug_counters(const pt_context *c, unsigned long long *out, i
 	return m;
 }
 
+/* debugging aid (not in the header): the render kernels' 1 / sqrt(x) (trace_device.cuh invSqrtExact) next to the IEEE routines */
+extern "C" int pt_debug_inv_sqrt(pt_context *c, uint32_t n, const float *x, float *fast, float *ieee)
+{
+	if (!c || !x || !fast || !ieee) return setError(PT_E_INVALID, "pt_debug_inv_sqrt: bad arguments");
+	CK(cudaSetDevice(c->device));
+	DevBuf dx, df, di;
+	CK(dx.alloc(size_t(n) * 4)); CK(df.alloc(size_t(n) * 4)); CK(di.alloc(size_t(n) * 4));
+	CK(cudaMemcpyAsync(dx.p, x, size_t(n) * 4, cudaMemcpyHostToDevice, c->stream));
+	launchInvSqrtCheck(n, dx.as<float>(), df.as<float>(), di.as<float>(), c->stream);
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(fast, df.p, size_t(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaMemcpyAsync(ieee, di.p, size_t(n) * 4, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	return PT_OK;
+}
+
 int pt_get_stats(const pt_context *c, pt_stats *out)
 {
 	if (!c || !out) return setError(PT_E_INVALID, "pt_get_stats: bad arguments");

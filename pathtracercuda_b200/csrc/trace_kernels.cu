@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 				// IEEE square root and division here, as in the reference's Camera::getRay: far from an object the quadratic of the
 				// primitive test cancels ~7 digits, so a direction that differs in its last bit re-rolls which silhouette pixels
 				// hit - with the exact direction (and toLocalOD's rounding order) the render kernel's first hits are the reference's
-				rd = cameraDir<true>(p.cam, u, v);
+				rd = cameraDir<2>(p.cam, u, v);
 				thr = mk(1.0f, 1.0f, 1.0f);
 				L = mk(0.0f, 0.0f, 0.0f);
 				bounce = 0;
@@ -531,6 +531,21 @@ __global__ void __launch_bounds__(kThreads) traceRaysKernel(SceneDev scene, uint
 			hitNormal[3 * i] = nn.x; hitNormal[3 * i + 1] = nn.y; hitNormal[3 * i + 2] = nn.z;
 		}
 	}
+}
+
+// debugging aid: invSqrtExact against the library routines it stands in for
+__global__ void invSqrtCheckKernel(uint32_t n, const float *x, float *fast, float *ieee)
+{
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+		fast[i] = invSqrtExact(x[i]);
+		ieee[i] = divExact(1.0f, sqrtExact(x[i]));
+	}
+}
+int launchInvSqrtCheck(uint32_t n, const float *x, float *fast, float *ieee, cudaStream_t stream)
+{
+	invSqrtCheckKernel<<<148 * 4, 256, 0, stream>>>(n, x, fast, ieee);
+	return 1;
 }
 
 // tonemap (kernels/tonemap.cu:4-27): mean -> Reinhard -> gamma 1/2.2 -> truncating RGBA8.  HBM-bound: 16 B in, 4 B out.

@@ -84,6 +84,7 @@ int launchTrace(const RenderParams &p, const LaunchConfig &cfg, cudaStream_t str
 int launchPrimary(const SceneDev &scene, const CameraDev &cam, uint32_t width, uint32_t height, int32_t *hitIndex, float *hitT, cudaStream_t stream);
 int launchTraceRays(const SceneDev &scene, size_t n, const float *origins, const float *directions, float tMin, int32_t *hitIndex, float *hitT,
                     float *hitNormal, cudaStream_t stream);
+int launchInvSqrtCheck(uint32_t n, const float *x, float *fast, float *ieee, cudaStream_t stream); // debugging aid
 int launchTonemap(const float4 *accum, uchar4 *out, uint32_t pixels, float invSampleCount, cudaStream_t stream);
 int launchScale(const float4 *accum, float4 *out, uint32_t pixels, float scale, cudaStream_t stream);
 

@@ -23,6 +23,7 @@ static inline float sqrtApprox(float x) { return sqrtf(x); }
 static inline float rsqrtApprox(float x) { return 1.0f / sqrtf(x); }
 static inline float divExact(float a, float b) { return a / b; }
 static inline float sqrtExact(float a) { return sqrtf(a); }
+static inline float invSqrtExact(float x) { return 1.0f / sqrtf(x); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 static inline float __uint2float_rn(uint32_t x) { return (float)x; }
@@ -152,7 +153,7 @@ void emu_first_hit(void *p, const pt_camera_desc *cd, uint32_t width, uint32_t h
 				                          (float(y) + 1.0f + m) * invH, beam, true, boxes);
 			const float u = (float(x) + 0.5f) / float(width), v = (float(y) + 0.5f) / float(height);
 			const V3 o = mk(cam.origin[0], cam.origin[1], cam.origin[2]);
-			const V3 d = cameraDir<kHotExact>(cam, u, v);
+			const V3 d = cameraDir<2>(cam, u, v);
 			const Hit h = closestHitWW<false, true, false, kHotExact>(sv, o, d, 0.001f, nv, pt, beam, nBeam, 0, boxes);
 			hitIndex[i] = h.prim < 0 ? -1 : int32_t(__float_as_uint(sv.prims[h.prim * 4 + 3].y));
 			hitT[i] = h.prim < 0 ? 0.0f : h.t;
@@ -220,7 +221,7 @@ uint64_t emu_render(void *p, const pt_camera_desc *cd, uint32_t width, uint32_t 
 				const uint4 r = philox4x32_10(pixel, sampleIdx, 0u, 0u, seedLo, seedHi);
 				const float u = (float(x) + uniform01(r.x)) * (1.0f / float(width)), v = (float(y) + uniform01(r.y)) * (1.0f / float(height));
 				uint32_t rz = r.z, rw = r.w;
-				V3 ro = camO, rd = cameraDir<kHotExact>(cam, u, v), thr = mk(1.0f, 1.0f, 1.0f), L = mk(0.0f, 0.0f, 0.0f);
+				V3 ro = camO, rd = cameraDir<2>(cam, u, v), thr = mk(1.0f, 1.0f, 1.0f), L = mk(0.0f, 0.0f, 0.0f);
 				uint32_t bounce = 0;
 				while (true)
 				{

@@ -517,3 +517,20 @@ def test_multi_gpu_context_through_the_c_abi(tmp_path):
         assert r.returncode == 0, r.stderr
     assert '"devices": 2' in r.stdout
     assert np.array_equal(imgio.read_png(a), imgio.read_png(b))
+
+
+def test_render_kernels_inverse_length_is_the_ieee_one():
+    """the camera-ray direction of the render kernels is normalised with the fast paths of the IEEE square root and division
+    (trace_device.cuh invSqrtExact, no range checks, no slow-path calls): bit for bit 1.0f / sqrtf(x) as the reference's
+    normalize() computes it - on the range a camera can produce and far beyond"""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(1.0, 6.0, 3_000_000), np.exp2(rng.uniform(-60, 60, 3_000_000)),
+                        np.nextafter(np.float32(1.0), np.float32(2.0)) * np.ones(1), [1.0, 2.0, 3.0, 4.0, 0.25, 1e-20, 1e20]]).astype(np.float32)
+    fast, ieee = np.zeros_like(x), np.zeros_like(x)
+    with pt.Pathtracer(8, 8) as P:
+        P.L.pt_debug_inv_sqrt.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        assert P.L.pt_debug_inv_sqrt(P.h, x.size, x.ctypes.data_as(C.c_void_p), fast.ctypes.data_as(C.c_void_p), ieee.ctypes.data_as(C.c_void_p)) == 0
+    host = (np.float32(1.0) / np.sqrt(x)).astype(np.float32)
+    assert np.array_equal(bits(ieee), bits(host))
+    assert np.array_equal(bits(fast), bits(ieee)), f"{(bits(fast) != bits(ieee)).sum()} of {x.size} differ"
