@@ -78,6 +78,26 @@ typedef struct pt_stats {
 	uint32_t scene_in_smem;/* 1 if the scene was staged into shared memory by TMA bulk copy */
 } pt_stats;
 
+/* What a reference CpuHittable still holds after its ctor (Hittable.h:41-59): the world->local rows (m_invTransformRow0..2),
+ * the world AABB (getAABB()), the type and the material - position / rotation / scale are gone.  pt_set_scene_xform takes
+ * that, so the reference's own SceneLoader.cpp can drive this library through an unmodified `class Pathtracer` interface
+ * (integration/Pathtracer_b200.cpp). */
+typedef struct pt_object_xform_desc {
+	uint32_t type;
+	float world_to_local[12]; /* three rows of four, as Hittable.h:22-24 */
+	float aabb_min[3];
+	float aabb_max[3];
+	pt_material_desc material;
+} pt_object_xform_desc;
+
+/* The four vectors Camera::getRay uses (Camera.h:15-18, Camera.inl:25-28): origin, lower-left corner, horizontal, vertical. */
+typedef struct pt_camera_vectors {
+	float origin[3];
+	float lower_left[3];
+	float horizontal[3];
+	float vertical[3];
+} pt_camera_vectors;
+
 typedef struct pt_context pt_context;
 
 /* Pathtracer::Pathtracer(width, height, openglPixelBuffer = 0)   Pathtracer.h:15, Pathtracer.cpp:30-68.
@@ -109,6 +129,10 @@ int pt_get_multi_info(const pt_context *ctx, int *devices, int *peer_to_peer, fl
  * BVH, replaces the previous scene.  count == 0 prints the reference's message and is a no-op returning PT_OK. */
 int pt_set_scene(pt_context *ctx, size_t count, const pt_object_desc *objects);
 
+/* Pathtracer::setScene for callers that hold reference CpuHittables (see pt_object_xform_desc): same semantics as
+ * pt_set_scene, the transforms and boxes are taken as given instead of being derived from position / rotation / scale. */
+int pt_set_scene_xform(pt_context *ctx, size_t count, const pt_object_xform_desc *objects);
+
 /* Pathtracer::loadTexture(path)   Pathtracer.h:35, Pathtracer.cpp:234-292.  Returns a 1-based handle, 0 on failure or
  * when 64 textures exist.  ".hdr" (Radiance RGBE) -> float RGBA, anything else (PNG) -> 8-bit RGBA. */
 uint32_t pt_load_texture(pt_context *ctx, const char *path);
@@ -121,6 +145,10 @@ int pt_set_skybox(pt_context *ctx, uint32_t handle);
 /* Pathtracer::render(camera, spp, ignoreHistory)   Pathtracer.h:26, Pathtracer.cpp:162-227.  Synchronous.  Adds `spp`
  * samples per pixel to the accumulation (or restarts it).  spp == 0 or no scene -> no kernel. */
 int pt_render(pt_context *ctx, const pt_camera_desc *camera, uint32_t spp, int ignore_history);
+
+/* Pathtracer::render for callers that hold a reference Camera object: its four ray vectors as they stand (pt_camera_vectors),
+ * no re-derivation from position / look-at / fovy. */
+int pt_render_vectors(pt_context *ctx, const pt_camera_vectors *camera, uint32_t spp, int ignore_history);
 
 /* Pathtracer::getTiming()   Pathtracer.h:29, Pathtracer.cpp:229-232.  GPU ms of the last pt_render. */
 float pt_get_timing_ms(const pt_context *ctx);

@@ -30,6 +30,8 @@ def load_library():
         "pt_get_multi_info": (i32, [vp, vp, vp, vp, vp]),
         "pt_destroy": (None, [vp]),
         "pt_set_scene": (i32, [vp, sz, vp]),
+        "pt_set_scene_xform": (i32, [vp, sz, vp]),
+        "pt_render_vectors": (i32, [vp, vp, u32, i32]),
         "pt_load_texture": (u32, [vp, cp]),
         "pt_load_texture_mem": (u32, [vp, u32, u32, i32, vp]),
         "pt_set_skybox": (i32, [vp, u32]),
@@ -65,7 +67,7 @@ def load_library():
     return L
 
 
-EXPORTS = ["pt_create", "pt_create_multi", "pt_get_multi_info", "pt_destroy", "pt_set_scene", "pt_load_texture", "pt_load_texture_mem", "pt_set_skybox", "pt_render",
+EXPORTS = ["pt_create", "pt_create_multi", "pt_get_multi_info", "pt_destroy", "pt_set_scene", "pt_set_scene_xform", "pt_render_vectors", "pt_load_texture", "pt_load_texture_mem", "pt_set_skybox", "pt_render",
            "pt_get_timing_ms", "pt_get_hdr", "pt_get_hdr_mean", "pt_get_hdr_sum", "pt_get_ldr", "pt_set_option", "pt_get_stats", "pt_camera_rotate", "pt_camera_translate", "pt_primary_pass",
            "pt_trace_rays", "pt_get_first_hit", "pt_accum_device_ptr", "pt_set_accum_device_ptr", "pt_load_scene_file", "pt_parse_scene_file",
            "pt_write_png", "pt_write_hdr", "pt_read_image", "pt_free", "pt_last_error", "pt_version"]

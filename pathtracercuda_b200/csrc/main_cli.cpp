@@ -7,6 +7,7 @@
 // --gpus N (devices 0..N-1) or --devices MASK, --partition pixels|samples, --exchange p2p|nccl (pt_create_multi).
 #include "../../include/pt_b200.h"
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -112,8 +113,14 @@ static void die(const char *what)
 	exit(EXIT_FAILURE);
 }
 
+static double nowMs()
+{
+	return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int main(int argc, char *argv[])
 {
+	const double t0 = nowMs();
 	Params params;
 	if (!processArgs(argc, argv, params)) return EXIT_SUCCESS;
 
@@ -141,6 +148,7 @@ int main(int argc, char *argv[])
 		pt_set_option(ctx, "exchange", (double)params.exchange);
 	}
 	else if (pt_create(params.m_width, params.m_height, params.device, &ctx) != PT_OK) die("pt_create");
+	const double tCreate = nowMs();
 	pt_set_option(ctx, "seed", (double)params.seed);
 	// reference-compatible normalisation: the reference renders 8 samples per render() call and divides by the number
 	// of CALLS (quirk Q1); one launch here counts as ceil(spp/8) calls.  --true-mean writes the real mean instead.
@@ -152,10 +160,12 @@ int main(int argc, char *argv[])
 	if (lr == PT_E_PARSE) { printf("%s", pt_last_error()); return EXIT_FAILURE; }      // printf(ex.what())
 	if (lr != PT_OK) die("pt_load_scene_file");
 
+	const double tLoad = nowMs();
 	const unsigned int slice = params.slice ? params.slice : params.m_spp;
 	float totalGpuTime = 0.0f, totalTrace = 0.0f, totalExchange = 0.0f;
 	unsigned long long totalRays = 0;
 	unsigned int nextReport = 0;
+	pt_stats st;
 	for (unsigned int i = 0; i < params.m_spp; i += slice)
 	{
 		const unsigned int spp = std::min(i + slice, params.m_spp) - i;
@@ -167,23 +177,11 @@ int main(int argc, char *argv[])
 		pt_get_multi_info(ctx, nullptr, nullptr, &tr, &ex);
 		totalTrace += tr;
 		totalExchange += ex;
-		pt_stats st;
 		pt_get_stats(ctx, &st);
 		totalRays += st.rays;
 	}
+	const double tRender = nowMs();
 	printf("Finished accumulating %d samples in %f ms GPU time\n", (int)params.m_spp, totalGpuTime);
-	if (params.stats)
-	{
-		pt_stats st;
-		pt_get_stats(ctx, &st);
-		int devices = 1, p2p = 0;
-		pt_get_multi_info(ctx, &devices, &p2p, nullptr, nullptr);
-		printf("{\"rays\": %llu, \"rays_last_launch\": %llu, \"samples_last_launch\": %llu, \"bvh_nodes\": %u, \"bvh_depth\": %u, \"scene_bytes\": %u, \"scene_in_smem\": %u, "
-		       "\"devices\": %d, \"partition\": \"%s\", \"exchange\": \"%s\", \"trace_ms\": %f, \"exchange_ms\": %f, \"exchange_bytes_per_device\": %llu}\n",
-		       totalRays, (unsigned long long)st.rays, (unsigned long long)st.samples, st.bvh_nodes, st.bvh_depth, st.scene_bytes, st.scene_in_smem, devices,
-		       params.partition ? "samples" : "pixels", devices == 1 ? "none" : (p2p ? "p2p" : "nccl"), totalTrace, totalExchange,
-		       (unsigned long long)(devices == 1 ? 0ull : (p2p ? (unsigned long long)params.m_width * params.m_height * 16ull / devices : (unsigned long long)params.m_width * params.m_height * 16ull)));
-	}
 
 	if (params.m_outputFilepath)
 	{
@@ -203,6 +201,19 @@ int main(int argc, char *argv[])
 			r = pt_write_png(params.m_outputFilepath, params.m_width, params.m_height, img);
 		}
 		if (r != PT_OK) printf("Failed to write file!\n");
+	}
+	const double tOut = nowMs();
+	if (params.stats)
+	{
+		int devices = 1, p2p = 0;
+		pt_get_multi_info(ctx, &devices, &p2p, nullptr, nullptr);
+		const unsigned long long imageBytes = (unsigned long long)params.m_width * params.m_height * 16ull;
+		printf("{\"rays\": %llu, \"rays_last_launch\": %llu, \"samples_last_launch\": %llu, \"bvh_nodes\": %u, \"bvh_depth\": %u, \"scene_bytes\": %u, \"scene_in_smem\": %u, "
+		       "\"devices\": %d, \"partition\": \"%s\", \"exchange\": \"%s\", \"trace_ms\": %f, \"exchange_ms\": %f, \"exchange_bytes_per_device\": %llu, "
+		       "\"host_ms\": {\"create\": %.1f, \"load_scene\": %.1f, \"render\": %.1f, \"read_back_and_write\": %.1f}}\n",
+		       totalRays, (unsigned long long)st.rays, (unsigned long long)st.samples, st.bvh_nodes, st.bvh_depth, st.scene_bytes, st.scene_in_smem, devices,
+		       params.partition ? "samples" : "pixels", devices == 1 ? "none" : (p2p ? "p2p" : "nccl"), totalTrace, totalExchange,
+		       devices == 1 ? 0ull : (p2p ? imageBytes / devices : imageBytes), tCreate - t0, tLoad - tCreate, tRender - tLoad, tOut - tRender);
 	}
 	pt_destroy(ctx);
 	return EXIT_SUCCESS;

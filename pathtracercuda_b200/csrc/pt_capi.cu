@@ -322,6 +322,38 @@ int pt_set_scene(pt_context *c, size_t count, const pt_object_desc *objects)
 	PT_CATCH(PT_E_LIMIT)
 }
 
+int pt_set_scene_xform(pt_context *c, size_t count, const pt_object_xform_desc *objects)
+{
+	PT_TRY
+	if (!c) return setError(PT_E_INVALID, "pt_set_scene_xform: null context");
+	if (count == 0)
+	{
+		printf("Setting an empty scene is not allowed!\n"); // Pathtracer.cpp:115
+		return PT_OK;
+	}
+	if (!objects) return setError(PT_E_INVALID, "pt_set_scene_xform: null objects");
+	std::vector<pt_object_desc> descs(count);
+	std::vector<ObjectXform> xf(count);
+	for (size_t i = 0; i < count; ++i)
+	{
+		memset(&descs[i], 0, sizeof descs[i]);
+		descs[i].type = objects[i].type;
+		descs[i].scale[0] = descs[i].scale[1] = descs[i].scale[2] = 1.0f;
+		descs[i].material = objects[i].material;
+		memset(&xf[i], 0, sizeof xf[i]);
+		memcpy(xf[i].w2l, objects[i].world_to_local, sizeof xf[i].w2l);
+		memcpy(xf[i].bmin, objects[i].aabb_min, 12);
+		memcpy(xf[i].bmax, objects[i].aabb_max, 12);
+	}
+	CompiledScene cs;
+	std::string err;
+	if (!compileScene(count, descs.data(), c->maxLeaf, cs, err, c->maxGlobal, xf.data())) return setError(PT_E_LIMIT, "pt_set_scene_xform: " + err);
+	int r = uploadScene(c, cs);
+	for (size_t i = 0; r == PT_OK && i < c->peers.size(); ++i) r = uploadScene(c->peers[i], cs);
+	return r;
+	PT_CATCH(PT_E_LIMIT)
+}
+
 // device copy of the texture table; with tex_unit = 0 the texture objects are left out and the kernels filter in software
 static int uploadTextureTable(pt_context *c)
 {
@@ -442,7 +474,7 @@ static SceneDev sceneDev(const pt_context *c)
 	return s;
 }
 
-static int renderOne(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ignore_history)
+static int renderOne(pt_context *c, const CameraDev *camera, uint32_t spp, int ignore_history)
 {
 	PT_TRY
 	if (!c || !camera) return setError(PT_E_INVALID, "pt_render: bad arguments");
@@ -461,7 +493,7 @@ static int renderOne(pt_context *c, const pt_camera_desc *camera, uint32_t spp, 
 	{
 		RenderParams p;
 		p.scene = sceneDev(c);
-		computeCamera(*camera, p.cam);
+		p.cam = *camera;
 		p.accum = c->accum;
 		p.counters = c->counters;
 		p.width = c->width;
@@ -601,7 +633,7 @@ static int loadNccl(pt_context *c)
 // on its own host thread, and the image comes together on the root either by itself - pixel partition with peer access: the
 // kernels of the other devices store their pixels straight into the root's accumulation buffer over NVLink, 16 bytes per
 // pixel, no collective at all - or by ONE ncclReduce of the float4 accumulation buffers (option "exchange").
-static int renderMulti(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ignore_history)
+static int renderMulti(pt_context *c, const CameraDev *camera, uint32_t spp, int ignore_history)
 {
 	std::vector<pt_context *> all = { c };
 	all.insert(all.end(), c->peers.begin(), c->peers.end());
@@ -725,7 +757,22 @@ int pt_render(pt_context *c, const pt_camera_desc *camera, uint32_t spp, int ign
 {
 	PT_TRY
 	if (!c || !camera) return setError(PT_E_INVALID, "pt_render: bad arguments");
-	return c->peers.empty() ? renderOne(c, camera, spp, ignore_history) : renderMulti(c, camera, spp, ignore_history);
+	CameraDev cam;
+	computeCamera(*camera, cam);
+	return c->peers.empty() ? renderOne(c, &cam, spp, ignore_history) : renderMulti(c, &cam, spp, ignore_history);
+	PT_CATCH(PT_E_LIMIT)
+}
+
+int pt_render_vectors(pt_context *c, const pt_camera_vectors *camera, uint32_t spp, int ignore_history)
+{
+	PT_TRY
+	if (!c || !camera) return setError(PT_E_INVALID, "pt_render_vectors: bad arguments");
+	CameraDev cam;
+	memcpy(cam.origin, camera->origin, 12);
+	memcpy(cam.lowerLeft, camera->lower_left, 12);
+	memcpy(cam.horizontal, camera->horizontal, 12);
+	memcpy(cam.vertical, camera->vertical, 12);
+	return c->peers.empty() ? renderOne(c, &cam, spp, ignore_history) : renderMulti(c, &cam, spp, ignore_history);
 	PT_CATCH(PT_E_LIMIT)
 }
 

@@ -357,7 +357,7 @@ struct Builder
 };
 } // namespace
 
-bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf, CompiledScene &out, std::string &err, uint32_t maxGlobal)
+bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf, CompiledScene &out, std::string &err, uint32_t maxGlobal, const ObjectXform *given)
 {
 	out = CompiledScene();
 	if (count == 0) { err = "empty scene"; return false; }
@@ -369,7 +369,8 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 #pragma omp parallel for schedule(static) if (count > 4096)
 	for (long i = 0; i < long(count); ++i)
 	{
-		computeObjectXform(objects[i], xf[i]);
+		if (given) xf[i] = given[i];
+		else computeObjectXform(objects[i], xf[i]);
 		for (int k = 0; k < 3; ++k)
 		{
 			bp[i].box.mn[k] = xf[i].bmin[k];

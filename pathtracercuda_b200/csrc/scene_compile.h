@@ -35,7 +35,10 @@ void computeObjectXform(const pt_object_desc &d, ObjectXform &out);
 
 // Build the BVH (binned SAH, kBins bins, centroid bounds, leaf when cheaper) and flatten it.
 // maxLeaf in [1, kMaxLeafPrims].  Returns false and sets err on failure (depth over kStackSize).
-bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf, CompiledScene &out, std::string &err, uint32_t maxGlobal = kMaxGlobalPrims);
+// `given` != nullptr: the objects' transforms and world boxes as the caller has them (pt_set_scene_xform: only w2l, bmin, bmax
+// are read) instead of deriving them from position / rotation / scale.
+bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf, CompiledScene &out, std::string &err, uint32_t maxGlobal = kMaxGlobalPrims,
+                  const ObjectXform *given = nullptr);
 
 // Camera ctor + update() equivalent (reference Camera.inl:4-23,54-62)
 void computeCamera(const pt_camera_desc &c, CameraDev &out);

@@ -534,3 +534,30 @@ def test_render_kernels_inverse_length_is_the_ieee_one():
     host = (np.float32(1.0) / np.sqrt(x)).astype(np.float32)
     assert np.array_equal(bits(ieee), bits(host))
     assert np.array_equal(bits(fast), bits(ieee)), f"{(bits(fast) != bits(ieee)).sum()} of {x.size} differ"
+
+
+@pytest.mark.parametrize("scene,fmt", [("generated_scene", "hdr"), ("cornell_box", "png")])
+def test_reference_front_end_on_our_back_end(scene, fmt, tmp_path):
+    """oracle/_ref/ref_main_b200 = the reference's UNMODIFIED main.cpp + SceneLoader.cpp + Hittable.cpp + image writers, linked
+    with integration/Pathtracer_b200.cpp (class Pathtracer over the C ABI) and libpt_b200.so instead of Pathtracer.cpp / BVH.cpp /
+    kernels/*.cu.  It renders the bundled scenes - its own argument parsing, JSON loader, texture requests, 8-spp render loop,
+    normalisation and file writers - and the image is the one our own command line writes for the same 8-spp slicing, bit for
+    bit; and within noise of the reference program proper."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_main_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_main_b200 not built (oracle/Makefile needs /root/reference)")
+    W, H, spp = 256, 144, 64
+    outs = {}
+    for tag, cmd in (("shim", [exe]), ("cli", [CLI, "--slice", "8"]), ("ref", [orc.REF_PT])):
+        if tag == "ref" and not os.path.exists(orc.REF_PT):
+            continue
+        out = str(tmp_path / f"{tag}.{fmt}")
+        r = subprocess.run(cmd + ["-w", str(W), "-h", str(H), "-spp", str(spp)] + (["-ohdr"] if fmt == "hdr" else []) + ["-o", out, f"scenes/{scene}.json"],
+                           cwd=pt.ASSETS, capture_output=True, text=True)
+        assert r.returncode == 0 and os.path.exists(out), (tag, r.stdout[-300:], r.stderr[-300:])
+        assert f"Finished accumulating {spp} samples in " in r.stdout
+        outs[tag] = imgio.read_hdr(out) if fmt == "hdr" else imgio.read_png(out)
+    assert np.array_equal(outs["shim"], outs["cli"])
+    if "ref" in outs:
+        a, b = outs["shim"][..., :3].astype(np.float64), outs["ref"][..., :3].astype(np.float64)
+        assert abs(a.mean() / b.mean() - 1) < 0.02
