@@ -176,10 +176,9 @@ int pt_create(uint32_t width, uint32_t height, int device, pt_context **out)
 	CKC(cudaEventCreate(&c->evStop));
 	CKC(cudaMalloc(&c->accum, px * sizeof(float4)));
 	CKC(cudaMemsetAsync(c->accum, 0, px * sizeof(float4), c->stream));
-	CKC(cudaMalloc(&c->scaledDev, px * sizeof(float4)));
-	CKC(cudaMalloc(&c->ldrDev, px * sizeof(uchar4)));
-	CKC(cudaMallocHost(&c->hostHdr, px * sizeof(float4)));
-	CKC(cudaMallocHost(&c->hostLdr, px * sizeof(uchar4)));
+	// (the read-back buffers - device staging and pinned host memory for the HDR and the LDR image - are allocated by the first
+	// getter that needs them: pinned allocations are slow, a peer context of a multi-GPU job never reads back, and a run that
+	// writes a PNG does not need the 33 MB HDR pair)
 	CKC(cudaMalloc(&c->counters, kCtrCount * sizeof(unsigned long long)));
 	CKC(cudaMalloc(&c->texDev, kMaxTextures * sizeof(TexDesc)));
 	CKC(cudaMemsetAsync(c->texDev, 0, kMaxTextures * sizeof(TexDesc), c->stream));
@@ -782,6 +781,12 @@ static const float *readHdr(pt_context *c, float scale)
 {
 	if (cudaSetDevice(c->device) != cudaSuccess) return nullptr;
 	const uint32_t px = c->width * c->height;
+	if ((!c->scaledDev && cudaMalloc(&c->scaledDev, size_t(px) * sizeof(float4)) != cudaSuccess) ||
+	    (!c->hostHdr && cudaMallocHost(&c->hostHdr, size_t(px) * sizeof(float4)) != cudaSuccess))
+	{
+		setError(PT_E_CUDA, std::string("pt_get_hdr: ") + cudaGetErrorString(cudaGetLastError()));
+		return nullptr;
+	}
 	launchScale(c->imageSource ? c->imageSource : c->accum, c->scaledDev, px, scale, c->stream);
 	if (cudaMemcpyAsync(c->hostHdr, c->scaledDev, size_t(px) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
 	    cudaStreamSynchronize(c->stream) != cudaSuccess)
@@ -815,6 +820,12 @@ const uint8_t *pt_get_ldr(pt_context *c)
 	if (!c) return nullptr;
 	if (cudaSetDevice(c->device) != cudaSuccess) return nullptr;
 	const uint32_t px = c->width * c->height;
+	if ((!c->ldrDev && cudaMalloc(&c->ldrDev, size_t(px) * sizeof(uchar4)) != cudaSuccess) ||
+	    (!c->hostLdr && cudaMallocHost(&c->hostLdr, size_t(px) * sizeof(uchar4)) != cudaSuccess))
+	{
+		setError(PT_E_CUDA, std::string("pt_get_ldr: ") + cudaGetErrorString(cudaGetLastError()));
+		return nullptr;
+	}
 	// tonemap.cu:17 divides by float(accumulatedSampleCount) via reciprocal-multiply; 0 frames -> division by zero in the
 	// reference; here the accumulation is zero in that case and the scale is clamped like getHDRImageData's
 	launchTonemap(c->imageSource ? c->imageSource : c->accum, c->ldrDev, px, 1.0f / fmaxf(float(c->accumulatedFrames), 1.0f), c->stream);

@@ -2,6 +2,7 @@
 #pragma once
 #define PTB_PRIM_FN __device__ __noinline__ // one out-of-line primitive test per kernel (code size, see trace_device.cuh)
 #define PTB_BEAM_FN __device__ __noinline__ // once per pixel: kept out of the hot loop's code
+#define PTB_ATAN_FN static __device__ __noinline__ // five call sites (sky lookup, sphere / cylinder UV): one copy, the hot loop has to stay small (instruction fetch)
 #include "trace_device.cuh"
 
 namespace ptb

@@ -132,6 +132,13 @@ static __device__ __noinline__ void sortSamples(uint32_t pixel, const RenderPara
 	__syncwarp();
 }
 
+// option "jitter" = 0: u = (x + 0.5) / W with the IEEE division of the reference's primary pass (cold, kept out of the hot loop)
+static __device__ __noinline__ void pixelCentreUV(float px, float py, uint32_t width, uint32_t height, float &u, float &v)
+{
+	u = divExact(px + 0.5f, float(width));
+	v = divExact(py + 0.5f, float(height));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // the trace kernel
 // ---------------------------------------------------------------------------------------------------------------
@@ -342,7 +349,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 				}
 				float u = (pxf + uniform01(r.x)) * invW; // trace.cu:190
 				float v = (pyf + uniform01(r.y)) * invH;
-				if (p.noJitter) { u = divExact(pxf + 0.5f, float(p.width)); v = divExact(pyf + 0.5f, float(p.height)); } // the reference's primary-pass ray
+				if (p.noJitter) pixelCentreUV(pxf, pyf, p.width, p.height, u, v); // the reference's primary-pass ray (parity aid; out of line: cold)
 				rz = r.z; rw = r.w;
 				if constexpr (SHARE)
 				{

@@ -40,9 +40,39 @@ def synthetic_scene_dict(n, seed=1984, skybox="skybox.hdr"):
 
 
 def write_synthetic_scene(path, n, seed=1984, skybox="skybox.hdr"):
+    """the scene of synthetic_scene_dict as a JSON file - byte for byte what json.dump(..., separators=(",", ":")) writes, put
+    together by hand (a million-object scene through json.dump takes a minute)"""
+    rng = np.random.default_rng(seed)
+    side = int(math.ceil(math.sqrt(n)))
+    half = side / 2.0
+    d = float(max(half, 4.0))
+    r_ = repr
+    head = ('{"camera":{"position":[%s,%s,%s],"look_at":[0.0,0.0,0.0],"fovy":60.0},"skybox":%s,"objects":[' % (r_(d * 1.3), r_(d * 0.45 + 1.0), r_(d * 0.3), json.dumps(skybox))
+            + '{"name":"floor","type":"QUAD","position":[0.0,0.0,0.0],"rotation":[0.0,0.0,0.0],"scale":[%s,1.0,%s],' % (r_(float(half + 2.0)), r_(float(half + 2.0)))
+            + '"material":{"type":"LAMBERT","baseColor":[1.0,1.0,1.0],"emissive":[0.0,0.0,0.0],"roughness":1.0,"metalness":0.0,"texture":""}}')
+    u = rng.random((n, 16))
+    idx = np.arange(n)
+    px = (idx % side) - half + 0.9 * u[:, 0]
+    pz = (idx // side) - half + 0.9 * u[:, 1]
+    alb = u[:, 2:5] * u[:, 5:8]
+    rot = u[:, 9:12] * 360 - 180
+    sc = 0.1 + 0.2 * u[:, 12]
+    shape = (u[:, 8] * 7).astype(np.int64) % 7
+    mat = (u[:, 13] * 3).astype(np.int64) % 3
     with open(path, "w") as f:
-        json.dump(synthetic_scene_dict(n, seed, skybox), f, separators=(",", ":"))
-        f.write("\n")
+        f.write(head)
+        chunk = []
+        for i in range(n):
+            s = r_(float(sc[i]))
+            chunk.append(',{"name":"","type":"%s","position":[%s,0.30000000000000004,%s],"rotation":[%s,%s,%s],"scale":[%s,%s,%s],'
+                         '"material":{"type":"%s","baseColor":[%s,%s,%s],"emissive":[0.0,0.0,0.0],"roughness":%s,"metalness":%s,"texture":""}}'
+                         % (SHAPE_NAMES[shape[i]], r_(float(px[i])), r_(float(pz[i])), r_(float(rot[i, 0])), r_(float(rot[i, 1])), r_(float(rot[i, 2])), s, s, s,
+                            MATERIAL_NAMES[mat[i]], r_(float(alb[i, 0])), r_(float(alb[i, 1])), r_(float(alb[i, 2])), r_(float(u[i, 14])), "1.0" if u[i, 15] > 0.5 else "0.0"))
+            if len(chunk) == 65536:
+                f.write("".join(chunk))
+                chunk = []
+        f.write("".join(chunk))
+        f.write("]}\n")
 
 
 def synthetic_scene(n, width, height, seed=1984):
