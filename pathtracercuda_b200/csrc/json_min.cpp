@@ -1,4 +1,5 @@
 #include "json_min.h"
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #ifdef _OPENMP
@@ -122,7 +123,35 @@ struct Parser
 			for (; k < i && s[k] >= '0' && s[k] <= '9'; ++k) { mant = mant * 10 + unsigned(s[k] - '0'); if (mant) ++digits; }
 			if (k < i && s[k] == '.')
 				for (++k; k < i && s[k] >= '0' && s[k] <= '9'; ++k) { mant = mant * 10 + unsigned(s[k] - '0'); if (mant) ++digits; --exp10; }
-			if (digits > 15) fast = false;
+			const bool plainDecimal = !(k < i && (s[k] == 'e' || s[k] == 'E'));
+			if (digits > 15)
+			{
+				fast = false;
+				// 16 - 19 significant digits without an exponent (what printing a double with 17 digits gives - every number
+				// of a generated scene file): the value is the exact rational mant / 10^frac, rounded to double ONCE by a 128-bit
+				// integer division - no strtod (which was most of the loader's time on a million-object scene)
+				if (plainDecimal && digits <= 19 && exp10 >= -19)
+				{
+					static const unsigned long long p10u[20] = { 1ull, 10ull, 100ull, 1000ull, 10000ull, 100000ull, 1000000ull, 10000000ull, 100000000ull, 1000000000ull,
+						10000000000ull, 100000000000ull, 1000000000000ull, 10000000000000ull, 100000000000000ull, 1000000000000000ull, 10000000000000000ull,
+						100000000000000000ull, 1000000000000000000ull, 10000000000000000000ull };
+					const unsigned long long den = p10u[-exp10];
+					const unsigned __int128 num = (unsigned __int128)mant << 64;
+					const unsigned __int128 q = num / den, r = num % den;
+					const unsigned long long qh = (unsigned long long)(q >> 64), ql = (unsigned long long)q;
+					const int hb = qh ? 127 - __builtin_clzll(qh) : (ql ? 63 - __builtin_clzll(ql) : -1);
+					if (hb >= 54)
+					{
+						int shift = hb - 52;
+						unsigned long long m = (unsigned long long)(q >> shift);
+						const unsigned __int128 rem = q & ((((unsigned __int128)1) << shift) - 1), half = ((unsigned __int128)1) << (shift - 1);
+						if (rem > half || (rem == half && (r != 0 || (m & 1ull)))) { if (++m == (1ull << 53)) { m >>= 1; ++shift; } }
+						const double d = ldexp(double(m), shift - 64);
+						v.num = neg ? -d : d;
+						return true;
+					}
+				}
+			}
 			if (fast && k < i && (s[k] == 'e' || s[k] == 'E'))
 			{
 				++k;
@@ -289,6 +318,28 @@ bool Parser::value(JsonValue &v)
 		return ok;
 	}
 } // namespace
+
+bool parseJsonSpan(const char *text, size_t begin, size_t end, JsonValue &out)
+{
+	Parser p{ text, end };
+	p.i = begin;
+	p.depth = 2; // never large enough for the parallel array path to matter; keeps the nesting limit conservative
+	if (!p.value(out)) return false;
+	p.ws();
+	return p.i == end;
+}
+
+bool scanJsonNumber(const char *text, size_t n, size_t &i, double &value, bool &isFloat)
+{
+	Parser p{ text, n };
+	p.i = i;
+	JsonValue v;
+	if (!p.number(v)) return false;
+	i = p.i;
+	value = v.num;
+	isFloat = v.kind == JsonValue::Float;
+	return true;
+}
 
 bool parseJson(const std::string &text, JsonValue &out, std::string &err)
 {
