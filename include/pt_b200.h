@@ -193,8 +193,6 @@ const float *pt_get_hdr_sum(pt_context *ctx);
  *                    pixel (2^k cells of equal sample count, k <= 8; the cell is the top bits, the Philox draw the rest).  Same
  *                    expectation as the reference's plain draws (Material.inl:40-41), never more variance, and the lanes of a
  *                    warp scatter into the same cell (coherent traversal): 1 on, 0 off, -1 auto (default: on from 128 spp)
- *  "sort_samples"    alternative to "stratify" (used when that is off): hand a pixel's samples out in the order of their first
- *                    scattering direction (an order only: same Philox counters, same paths): 1 on, 0 off (default)
  *  "smem_stack"      traversal stack in shared memory instead of local memory: 1 / -1 (default) when it fits, 0 off
  *  "jitter"          0: every sample goes through the pixel centre, u = (x + 0.5) / W (parity aid; default 1 = trace.cu:190-191)
  *  "first_hit"       1: pt_render also records, per pixel, the scene index and t of the closest hit of the camera ray AS FOUND BY

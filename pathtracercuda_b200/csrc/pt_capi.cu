@@ -41,11 +41,10 @@ struct pt_context
 	float *hostHdr = nullptr;     // pinned
 	uint8_t *hostLdr = nullptr;   // pinned
 	unsigned long long *counters = nullptr;
-	void *sortScratch = nullptr; // per-warp sample order (RenderParams::sortScratch)
-	size_t sortScratchBytes = 0;
 	int32_t *firstHitIndex = nullptr; // option "first_hit": the render kernel's own first-hit (index, t) per pixel (parity aid)
 	float *firstHitT = nullptr;
 	bool firstHit = false, noJitter = false;
+	float *centreUV = nullptr; // option "jitter" = 0: pixel-centre coordinates (RenderParams::centreU / centreV), made on first use
 	// scene
 	float4 *sceneBlob = nullptr;
 	Mat *mats = nullptr;
@@ -261,9 +260,9 @@ void pt_destroy(pt_context *c)
 	if (c->hostHdr) cudaFreeHost(c->hostHdr);
 	if (c->hostLdr) cudaFreeHost(c->hostLdr);
 	if (c->counters) cudaFree(c->counters);
-	if (c->sortScratch) cudaFree(c->sortScratch);
 	if (c->firstHitIndex) cudaFree(c->firstHitIndex);
 	if (c->firstHitT) cudaFree(c->firstHitT);
+	if (c->centreUV) cudaFree(c->centreUV);
 	if (c->texDev) cudaFree(c->texDev);
 	if (c->sceneBlob) cudaFree(c->sceneBlob);
 	if (c->mats) cudaFree(c->mats);
@@ -524,42 +523,26 @@ static int renderOne(pt_context *c, const CameraDev *camera, uint32_t spp, int i
 			p.strataPer = spp >> k;
 			p.strataInvPer = 1.0f / float(p.strataPer);
 		}
-		p.sortScratch = nullptr;
-		p.sortStride = 0;
-		// round-1 alternative to the stratification: keep the plain Philox draws and SORT the pixel's samples by first scattering direction
-		const bool wantSort = !wantStrata && c->launch.sortSamples != 0 && spp <= 65535u && spp >= 64u;
-		if (wantSort)
-		{
-			// scratch for the per-pixel sample order: 2 x stride uint16 per warp of the (persistent) grid
-			const uint32_t stride = (spp + 127u) & ~127u;
-			const size_t warps = size_t(c->launch.smCount) * 2u * (1024u / 32u); // launchKernel: smCount x blocksPerSm (<= 2) CTAs of 32 warps
-			const size_t bytes = warps * size_t(stride) * (2u + 2u);             // order + keys per sample (sortSamples)
-			if (bytes > c->sortScratchBytes)
-			{
-				if (c->sortScratch) CK(cudaFree(c->sortScratch));
-				c->sortScratch = nullptr;
-				c->sortScratchBytes = 0;
-				CK(cudaMalloc(&c->sortScratch, bytes));
-				c->sortScratchBytes = bytes;
-			}
-			p.sortScratch = static_cast<uint16_t *>(c->sortScratch);
-			p.sortStride = stride;
-			p.sortIgnore = c->launch.sortSamples == 2 ? 1u : 0u;
-			// measured on generated_scene (ms per 4096 spp): 64 bins 576, 128 bins (4 + 3 bits) 569, 256 bins 570-573; 2048 spp: 297 / 295
-			p.sortBitsA = c->launch.sortBitsA > 0 ? uint32_t(c->launch.sortBitsA) : 4u;
-			p.sortBitsB = c->launch.sortBitsB >= 0 ? uint32_t(c->launch.sortBitsB) : (spp >= 2048u ? 3u : 2u);
-			const uint32_t major = p.sortBitsA & 16u;
-			uint32_t a = p.sortBitsA & 15u, b = p.sortBitsB;
-			if (a + b < 5u) a = 5u - b;
-			if (a + b > 7u) { a = 4u; b = 3u; }
-			p.sortBitsA = a | major;
-			p.sortBitsB = b;
-		}
 		p.beam = c->launch.beam < 0 ? (spp >= 128u ? 1u : 0u) : uint32_t(c->launch.beam != 0);
 		p.alpha = c->alpha;
-		p.noJitter = c->noJitter ? 1u : 0u;
+		if (c->noJitter)
+		{
+			if (!c->centreUV)
+			{
+				// (this file is compiled without FMA contraction: the division is the IEEE one of the reference's primary pass)
+				std::vector<float> uv(size_t(c->width) + c->height);
+				for (uint32_t x = 0; x < c->width; ++x) uv[x] = (float(x) + 0.5f) / float(c->width);
+				for (uint32_t y = 0; y < c->height; ++y) uv[c->width + y] = (float(y) + 0.5f) / float(c->height);
+				CK(cudaMalloc(&c->centreUV, uv.size() * sizeof(float)));
+				CK(cudaMemcpy(c->centreUV, uv.data(), uv.size() * sizeof(float), cudaMemcpyHostToDevice));
+			}
+			p.centreU = c->centreUV;
+			p.centreV = c->centreUV + c->width;
+			p.aids |= kAidPixelCentre;
+		}
 		p.firstHitIndex = c->firstHit ? c->firstHitIndex : nullptr;
 		p.firstHitT = c->firstHit ? c->firstHitT : nullptr;
+		if (c->firstHit) p.aids |= kAidFirstHit;
 		c->launch.stackLevels = int(c->bvhDepth) + 2;
 		CK(cudaEventRecord(c->evStart, c->stream)); // (all allocations are behind us: the events bracket the device work alone)
 		// pixel partition: the pixels of the other ranks hold zeros, so that the sum over ranks is the image
@@ -866,7 +849,6 @@ static int setOptionOne(pt_context *c, const char *key, double value)
 	else if (k == "max_global") c->maxGlobal = uint32_t(value < 0 ? 0 : value);
 	else if (k == "regen_low") c->launch.regenLow = int(value);
 	else if (k == "beam") c->launch.beam = int(value);
-	else if (k == "sort_samples") c->launch.sortSamples = int(value);
 	else if (k == "alpha") c->alpha = float(value);
 	else if (k == "stratify") c->launch.stratify = int(value);
 	else if (k == "strata_k") c->launch.strataK = value < 2 ? 0 : (value > 10 ? 10 : int(value));
@@ -885,8 +867,6 @@ static int setOptionOne(pt_context *c, const char *key, double value)
 			CK(cudaMemset(c->firstHitT, 0, px * 4));
 		}
 	}
-	else if (k == "sort_bits_a") c->launch.sortBitsA = int(value);
-	else if (k == "sort_bits_b") c->launch.sortBitsB = int(value);
 	else if (k == "tex_unit") { c->texUnit = value != 0; return uploadTextureTable(c); }
 	else return setError(PT_E_INVALID, "pt_set_option: unknown option " + k);
 	return PT_OK;

@@ -43,19 +43,29 @@ constexpr uint32_t kMaxGlobalPrims = 8;
 constexpr size_t kTopOrderNodes = 4096; // nodes[0..4096) are numbered breadth-first, the rest depth-first (scene_compile.cpp)
 constexpr float kGlobalAreaFraction = 0.25f;
 
-// One primitive = world->local 3x4 (the reference's Hittable rows, Hittable.h:22-24) + shape type + indices (64 B).
+// One primitive = world->local 3x4 (the reference's Hittable rows, Hittable.h:22-24) + one quad of shape data (64 B).
 // The 40 B material the reference embeds in every 96 B Hittable (Hittable.h:25) lives in its own table: it is
 // only needed once per path segment (at the closest hit), not once per candidate.
+// The fourth quad: the quadric's coefficients as the floats the intersection routine multiplies with (B, H, J of
+// A x^2 + B y^2 + C z^2 + H y + J = 0 with A = C = 1; zero for the other shapes) and ONE word with everything discrete, laid out
+// so that every decision of the primitive test is a single-bit test: no compare chains on the type, no int -> float conversions.
 struct alignas(16) Prim
 {
 	float row0[4];
 	float row1[4];
 	float row2[4];
-	uint32_t type;       // PT_SPHERE .. PT_CUBE
-	uint32_t sceneIndex; // index in the caller's object array (tie-break + primary-pass output)
-	uint32_t flags;      // bit0: textured (needs u,v)
-	uint32_t pad;
+	float qB, qH, qJ;
+	uint32_t packed; // kPrim* below
 };
+constexpr uint32_t kPrimSceneMask = 0x00ffffffu; // bits 0..23: index in the caller's object array (tie-break + primary-pass output)
+constexpr int kPrimTypeShift = 24;               // bits 24..26: PT_SPHERE .. PT_CUBE
+constexpr uint32_t kPrimTextured = 1u << 27;     // needs u, v
+constexpr uint32_t kPrimFlat = 1u << 28;         // disk or quad
+constexpr uint32_t kPrimCube = 1u << 29;
+constexpr uint32_t kPrimDisk = 1u << 30;
+constexpr uint32_t kPrimSphere = 1u << 31;
+constexpr uint32_t kMaxSceneObjects = kPrimSceneMask + 1u; // (a leaf reference holds 24 bits of primitive index as well)
+
 static_assert(sizeof(Prim) == 64, "Prim must be 64 bytes");
 
 // Material (reference Material.h:22-27, 40 B) padded to 48 B, with roughness already clamped (Material.inl:12).

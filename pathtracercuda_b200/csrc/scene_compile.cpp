@@ -11,6 +11,9 @@
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace ptb
 {
@@ -360,6 +363,10 @@ struct Builder
 bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf, CompiledScene &out, std::string &err, uint32_t maxGlobal, const ObjectXform *given)
 {
 	out = CompiledScene();
+	static const bool ptbTiming = getenv("PTB_TIMING") != nullptr;
+	auto tNow = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+	double tLast = tNow();
+	auto lap = [&](const char *what) { if (ptbTiming) { const double t = tNow(); fprintf(stderr, "  compileScene %-14s %7.1f ms\n", what, (t - tLast) * 1e3); tLast = t; } };
 	if (count == 0) { err = "empty scene"; return false; }
 	if (count > kLeafStartMask) { err = "too many objects"; return false; }
 	maxLeaf = std::max(1u, std::min(maxLeaf, kMaxLeafPrims));
@@ -380,6 +387,7 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 		bp[i].index = uint32_t(i);
 	}
 
+	lap("xforms");
 	// hoist the primitives that span the scene (pt_types.h kMaxGlobalPrims): largest first, at the front of the order
 	Box sceneBox;
 	sceneBox.reset();
@@ -400,7 +408,9 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 	}
 	out.globalCount = uint32_t(nGlobal);
 
+	lap("hoist");
 	out.nodes.assign(std::max<size_t>(count, 2) - 1 + 1, Node());
+	lap("alloc nodes");
 	Builder b(bp, out.nodes, maxLeaf, objects);
 	Box rootBox;
 	uint32_t depth = 0;
@@ -409,6 +419,7 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 #pragma omp single
 	root = b.build(nGlobal, count, rootBox, depth);
 
+	lap("build");
 	if (root < 0)
 	{
 		// the whole scene is one leaf: give it a root node whose second child is empty
@@ -462,7 +473,8 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 		}
 		if (order.size() != n) { err = "internal: BVH renumbering lost nodes"; return false; }
 		std::vector<Node> renum(n);
-		for (size_t k = 0; k < n; ++k)
+#pragma omp parallel for schedule(static) if (n > 8192)
+		for (long k = 0; k < long(n); ++k)
 		{
 			Node nd = out.nodes[order[k]];
 			for (int c = 0; c < 2; ++c)
@@ -471,6 +483,7 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 		}
 		out.nodes.swap(renum);
 	}
+	lap("renumber");
 	// the hoisted primitives' boxes, two per record, behind the tree: the pixel-beam walk decides with them which hoisted
 	// primitives the camera rays of a pixel have to test at all
 	out.treeNodeCount = uint32_t(out.nodes.size());
@@ -499,8 +512,11 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 	{
 		float scale = 0.0f;
 		for (int k = 0; k < 3; ++k) scale = std::max(scale, std::max(fabsf(sceneBox.mn[k]), fabsf(sceneBox.mx[k])));
-		for (Node &nd : out.nodes)
+		const long nn = long(out.nodes.size());
+#pragma omp parallel for schedule(static) if (nn > 8192)
+		for (long q = 0; q < nn; ++q)
 		{
+			Node &nd = out.nodes[size_t(q)];
 			float mm[12]; // as the builder left them: child c = min[3] max[3] at 6 * c
 			memcpy(mm, nd.f, sizeof mm);
 			for (int c = 0; c < 2; ++c)
@@ -524,6 +540,7 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 			}
 		}
 	}
+	lap("centre/half");
 	out.depth = depth;
 	out.leafCount = b.leafCount.load();
 	for (int k = 0; k < 3; ++k) { out.sceneMin[k] = sceneBox.mn[k]; out.sceneMax[k] = sceneBox.mx[k]; }
@@ -531,7 +548,8 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 
 	out.prims.resize(count);
 	out.mats.resize(count);
-	for (size_t i = 0; i < count; ++i)
+#pragma omp parallel for schedule(static) if (count > 8192)
+	for (long i = 0; i < long(count); ++i)
 	{
 		const uint32_t src = bp[i].index;
 		const pt_object_desc &d = objects[src];
@@ -539,10 +557,14 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 		memcpy(p.row0, xf[src].w2l[0], 16);
 		memcpy(p.row1, xf[src].w2l[1], 16);
 		memcpy(p.row2, xf[src].w2l[2], 16);
-		p.type = d.type <= PT_CUBE ? d.type : uint32_t(PT_SPHERE);
-		p.sceneIndex = src;
-		p.flags = d.material.texture != 0 ? 1u : 0u;
-		p.pad = 0;
+		const uint32_t type = d.type <= PT_CUBE ? d.type : uint32_t(PT_SPHERE);
+		// quadric coefficients: the template arguments of Hittable.inl:151 sphere <1,1,1,..,-1>, :176 cylinder <1,0,1,..,-1>, :242 cone <1,-1,1>,
+		// :273 paraboloid <1,0,1,..,H=-1>
+		p.qB = type == PT_SPHERE ? 1.0f : (type == PT_CONE ? -1.0f : 0.0f);
+		p.qH = type == PT_PARABOLOID ? -1.0f : 0.0f;
+		p.qJ = (type == PT_SPHERE || type == PT_CYLINDER) ? -1.0f : 0.0f;
+		p.packed = src | (type << kPrimTypeShift) | (d.material.texture != 0 ? kPrimTextured : 0u) | ((type == PT_DISK || type == PT_QUAD) ? kPrimFlat : 0u) |
+		           (type == PT_CUBE ? kPrimCube : 0u) | (type == PT_DISK ? kPrimDisk : 0u) | (type == PT_SPHERE ? kPrimSphere : 0u);
 		Mat &m = out.mats[i];
 		memcpy(m.baseColor, d.material.base_color, 12);
 		memcpy(m.emissive, d.material.emissive, 12);
@@ -552,6 +574,7 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 		m.type = d.material.type <= PT_LAMBERT_GGX ? d.material.type : uint32_t(PT_LAMBERT);
 		m.pad[0] = m.pad[1] = 0;
 	}
+	lap("records");
 	return true;
 }
 

@@ -2,7 +2,7 @@
 #pragma once
 #define PTB_PRIM_FN __device__ __noinline__ // one out-of-line primitive test per kernel (code size, see trace_device.cuh)
 #define PTB_BEAM_FN __device__ __noinline__ // once per pixel: kept out of the hot loop's code
-#define PTB_ATAN_FN static __device__ __noinline__ // five call sites (sky lookup, sphere / cylinder UV): one copy, the hot loop has to stay small (instruction fetch)
+#define PTB_ATAN_FN static __device__ __noinline__ // the texture-coordinate call sites (sphere / cylinder UV) share one copy; the sky lookup of the hot loop inlines its own
 #include "trace_device.cuh"
 
 namespace ptb
@@ -31,9 +31,6 @@ __device__ __forceinline__ void pixelToXY(uint32_t pixel, uint32_t width, uint32
 	else { px = pixel % width; py = pixel / width; }
 }
 
-// one out-of-line copy each of the bilinear texture tap and of Philox: both are used by two stages of every trace kernel
-static __device__ __noinline__ V3 texLookupNI(const TexDesc *textures, uint32_t handle, float u, float v) { return texLookup(textures, handle, u, v); }
-static __device__ __noinline__ uint4 philoxNI(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1) { return philox4x32_10(c0, c1, c2, 0u, k0, k1); }
 constexpr uint32_t kInvalid = 0xffffffffu;
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -8,9 +8,8 @@
 //     segments instead of idling until the longest path of the warp ends (the reference runs one thread per pixel with no
 //     compaction).  Long renders (SHARE + SPLIT, from 64 spp): ONE PIXEL PER WARP - the lanes trace samples of the same
 //     pixel; the leaves its camera rays can reach are found once per pixel (pixel beams, trace_device.cuh beamLeaves); a
-//     pass of the main loop is either for camera rays or for scattered rays; from 1024 spp the samples are handed out in
-//     the order of their first scattering direction (sortSamples below).  Short renders: one pixel per lane, pixels handed
-//     out by a warp-aggregated atomic (ballot + popc prefix);
+//     pass of the main loop is either for camera rays or for scattered rays; the first bounce is stratified (RenderParams::
+//     strataPer).  Short renders: one pixel per lane, pixels handed out by a warp-aggregated atomic (ballot + popc prefix);
 //   * no per-pixel RNG state, no 48 B/pixel buffer: Philox4x32-10 keyed on (seed), counter (pixel, sample, bounce slot);
 //   * the BVH is 64-byte two-box nodes + 64-byte primitives read with 128-bit loads; when nodes+primitives fit in
 //     shared memory they are staged there once per CTA with a TMA bulk copy (cp.async.bulk + mbarrier);
@@ -24,120 +23,6 @@
 
 namespace ptb
 {
-
-// ---------------------------------------------------------------------------------------------------------------
-// Sample order.  The lanes of a warp trace samples of one pixel; the scattered rays of the first bounce leave (nearly) the
-// same point, in directions set by the sample's first two BSDF randoms.  Handing the samples out in the order of those
-// randoms - 32..256 bins: lobe + azimuth (the top bits of the first), polar angle (the top bits of the second), neighbours adjacent -
-// puts similar directions into the same pass: similar walks, the same leaves, the same hit-or-miss outcome, the same lobe.
-// It is only an order: every sample is still drawn from its own Philox counter, so the estimator and the set of paths are
-// unchanged (the image differs by float summation order alone).  A counting sort by the warp, once per pixel: pass A
-// draws each sample's randoms and counts the bins (shared-memory atomics: only the counts are used), pass B gives every
-// sample its place (ranks from match_any, not from atomics, so the order is the same from run to run).  `order` and `keys` live in global scratch (L2).
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int kSortBinsMax = 128; // bins = 2^(bitsA + bitsB) <= 128, >= 32
-// Scratch of one warp (global memory, L2): order[stride] uint16 | keys[stride] uint16.  Four samples per lane and iteration
-// (s = base + 4 * lane + k): the four Philox evaluations are independent, the key loads and stores are vectors.
-// (Keeping the draws too, so that generating the camera ray reads slot 0 back instead of drawing it again, was measured:
-// 634 vs 574 ms - a dependent 16-byte gather from a 300 MB scratch at the head of every camera pass.)
-static __device__ __forceinline__ size_t sortScratchBytesPerWarp(uint32_t stride) { return size_t(stride) * (2u + 2u); }
-static __device__ __forceinline__ char *sortScratchOfWarp(const RenderParams &p)
-{
-	return reinterpret_cast<char *>(p.sortScratch) + (size_t(blockIdx.x) * (kTraceThreads / 32) + (threadIdx.x >> 5)) * sortScratchBytesPerWarp(p.sortStride);
-}
-// (two arguments on purpose: the call sits in the kernel's main loop, and every argument register is one the loop loses)
-static __device__ __noinline__ void sortSamples(uint32_t pixel, const RenderParams *pp, uint32_t *hist)
-{
-	const RenderParams &p = *pp;
-	const uint32_t spp = p.spp, sampleOffset = p.sampleOffset, sampleStride = p.sampleStride, seedLo = p.seedLo, seedHi = p.seedHi;
-	const uint32_t bitsA = p.sortBitsA, bitsB = p.sortBitsB;
-	char *mine = sortScratchOfWarp(p);
-	uint16_t *order = reinterpret_cast<uint16_t *>(mine);
-	uint16_t *keys = order + p.sortStride;
-	const uint32_t lane = threadIdx.x & 31u;
-	const uint32_t lt = (1u << lane) - 1u;
-	const uint32_t nbA = bitsA & 15u;
-	const uint32_t bins = 1u << (nbA + bitsB), perLane = bins >> 5;
-	for (uint32_t k = lane; k < bins; k += 32) hist[k] = 0;
-	__syncwarp();
-	// pass A: draws, keys, histogram
-	for (uint32_t base = 0; base < spp; base += 128)
-	{
-		const uint32_t s0 = base + 4u * lane;
-		uint32_t key[4];
-#pragma unroll
-		for (int k = 0; k < 4; ++k)
-		{
-			const uint32_t s = s0 + uint32_t(k);
-			key[k] = bins; // samples past the end: a bin of their own, never counted
-			if (s < spp)
-			{
-				const uint4 r = philox4x32_10(pixel, sampleOffset + s * sampleStride, 0u, 0u, seedLo, seedHi);
-				const uint32_t a = r.z >> (32u - nbA), bb = bitsB ? r.w >> (32u - bitsB) : 0u;
-				// snake through the minor bins: neighbouring keys are neighbouring directions
-				if (bitsA & 16u) key[k] = (bb << nbA) | ((bb & 1u) ? ((1u << nbA) - 1u) - a : a);
-				else key[k] = (a << bitsB) | ((a & 1u) ? ((1u << bitsB) - 1u) - bb : bb);
-			}
-		}
-		if (s0 < spp) __stcg(reinterpret_cast<uint2 *>(keys + s0), make_uint2(key[0] | (key[1] << 16), key[2] | (key[3] << 16))); // stride is a multiple of 128
-#pragma unroll
-		for (int k = 0; k < 4; ++k)
-			if (key[k] < bins) atomicAdd(&hist[key[k]], 1u); // only the COUNTS are used: no order dependence
-	}
-	__syncwarp();
-	// counts -> first position of every bin (lane l owns bins l * perLane ... + perLane - 1)
-	{
-		uint32_t sum = 0;
-		for (uint32_t k = 0; k < perLane; ++k) sum += hist[lane * perLane + k];
-		uint32_t incl = sum;
-#pragma unroll
-		for (int o = 1; o < 32; o <<= 1)
-		{
-			const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-			if (int(lane) >= o) incl += t;
-		}
-		uint32_t run = incl - sum;
-		__syncwarp();
-		for (uint32_t k = 0; k < perLane; ++k)
-		{
-			const uint32_t c = hist[lane * perLane + k];
-			hist[lane * perLane + k] = run;
-			run += c;
-		}
-		__syncwarp();
-	}
-	// pass B: places.  Stable in the order (k, lane) within a 128-sample batch - any fixed order will do, it is the same from run to run
-	for (uint32_t base = 0; base < spp; base += 128)
-	{
-		const uint32_t s0 = base + 4u * lane;
-		uint2 packed = make_uint2(bins | (bins << 16), bins | (bins << 16));
-		if (s0 < spp) packed = __ldcg(reinterpret_cast<const uint2 *>(keys + s0));
-		const uint32_t key[4] = { packed.x & 0xffffu, packed.x >> 16, packed.y & 0xffffu, packed.y >> 16 };
-#pragma unroll
-		for (int k = 0; k < 4; ++k)
-		{
-			const uint32_t same = __match_any_sync(0xffffffffu, key[k]);
-			uint32_t first = 0;
-			if (key[k] < bins) first = hist[key[k]];
-			__syncwarp();
-			if (key[k] < bins)
-			{
-				order[first + uint32_t(__popc(same & lt))] = uint16_t(s0 + uint32_t(k));
-				if ((same & lt) == 0u) hist[key[k]] = first + uint32_t(__popc(same));
-			}
-			__syncwarp();
-		}
-	}
-	__threadfence_block();
-	__syncwarp();
-}
-
-// option "jitter" = 0: u = (x + 0.5) / W with the IEEE division of the reference's primary pass (cold, kept out of the hot loop)
-static __device__ __noinline__ void pixelCentreUV(float px, float py, uint32_t width, uint32_t height, float &u, float &v)
-{
-	u = divExact(px + 0.5f, float(width));
-	v = divExact(py + 0.5f, float(height));
-}
 
 // ---------------------------------------------------------------------------------------------------------------
 // the trace kernel
@@ -172,11 +57,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 	__shared__ BeamEntry beamList[SHARE && TRAV >= 1 ? kTraceThreads / 32 : 1][kBeamMax];
 	__shared__ BeamBox beamBoxes[SHARE && TRAV >= 1 && !SMEM ? kTraceThreads / 32 : 1][kBeamMax]; // scenes in global memory: the leaves' boxes (trace_device.cuh BeamBox)
 	int nBeam = -1;
-	// SPLIT: per-warp bin counters of sortSamples, and the warp's slice of the sample-order scratch
 	__shared__ float2 pixelXY[SHARE ? kTraceThreads / 32 : 1]; // SHARE: (x, y) of the warp's pixel, once per pixel instead of once per sample
-	__shared__ uint32_t sortHist[SPLIT ? kTraceThreads / 32 : 1][SPLIT ? kSortBinsMax : 1];
-	// (the warp's slice of the scratch is recomputed where it is used: two pointers kept live cost four registers)
-	auto warpScratch = [&]() -> char * { return sortScratchOfWarp(p); };
 
 	const uint32_t lane = threadIdx.x & 31u;
 	// the work counter hands out LOCAL indices: pixel = local * pixelStride + pixelOffset (all pixels for stride 1)
@@ -199,31 +80,33 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 	while (true)
 	{
 		bool generate;
+		uint32_t nGen = 0; // SHARE: lanes that start a new sample in this pass (warp-uniform)
 		if constexpr (SHARE)
 		{
 			// ---- the 32 lanes of the warp work on the SAME pixel: a lane without a path takes the pixel's next sample.
 			// Camera rays of one warp are then (nearly) the same ray, the first hits the same primitive, the scattered rays
 			// start from the same place: coherent node fetches (shared-memory broadcast) and fewer divergent branches ----
 			generate = false;
+			nGen = 0;
 			const uint32_t needMask = __ballot_sync(0xffffffffu, !alive);
 			if (needMask)
 			{
 				// hand out new samples only to groups of >= regenLow idle lanes (or when nobody is left tracing): the camera
-				// rays of one group are nearly the same ray and stay in step through their first hit
-				if (pixel != kInvalid && wNext < p.spp && (uint32_t(__popc(needMask)) >= p.regenLow || needMask == 0xffffffffu || p.spp - wNext < 32u))
+				// rays of one group are nearly the same ray and stay in step through their first hit.  Everything here but the
+				// lane's own place in the group is warp-uniform: one vote per pass, the rest is arithmetic on its result
+				const uint32_t idle = uint32_t(__popc(needMask));
+				if (pixel != kInvalid && wNext < p.spp && (idle >= p.regenLow || needMask == 0xffffffffu || p.spp - wNext < 32u))
 				{
-					const uint32_t mine = wNext + __popc(needMask & ((1u << lane) - 1u));
-					if (!alive && mine < p.spp)
+					nGen = min(idle, p.spp - wNext);
+					const uint32_t place = __popc(needMask & ((1u << lane) - 1u));
+					if (!alive && place < nGen)
 					{
-						sample = mine;
-						if constexpr (SPLIT)
-							if (p.sortScratch != nullptr && !p.sortIgnore) // the pixel's samples in the order of their first scattering direction
-								sample = __ldcg(reinterpret_cast<const uint16_t *>(warpScratch()) + mine);
+						sample = wNext + place;
 						generate = true;
 					}
-					wNext = min(p.spp, wNext + uint32_t(__popc(needMask)));
+					wNext += nGen;
 				}
-				if (!__any_sync(0xffffffffu, alive || generate))
+				if (needMask == 0xffffffffu && nGen == 0u)
 				{
 					// the pixel is complete: add the lanes' partial sums in a fixed order (butterfly), one lane writes
 					if (pixel != kInvalid)
@@ -258,13 +141,6 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 						pixelToXY(pixel, p.width, p.height, px, py);
 						if (lane == 0) pixelXY[threadIdx.x >> 5] = make_float2(float(px), float(py));
 						__syncwarp();
-					}
-					if constexpr (SPLIT)
-					{
-						if (p.sortScratch != nullptr)
-						{
-							sortSamples(pixel, &p, sortHist[threadIdx.x >> 5]);
-						}
 					}
 					if constexpr (TRAV >= 1)
 					{
@@ -320,7 +196,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 			// SPLIT: a pass is EITHER for the camera rays just generated (coherent: same pixel, leaves from the pixel's beam list,
 			// no tree walk, usually the same material) OR for the scattered rays, where every live lane then walks the tree
 			// together.  Mixed passes kept ~11 of 32 lanes in the node loop: the lanes with camera rays had nothing to walk.
-			if (__any_sync(0xffffffffu, generate)) takePart = generate;
+			if (SHARE ? nGen != 0u : __any_sync(0xffffffffu, generate)) takePart = generate;
 		}
 		// COUNT + SPLIT: passes, participating lanes and clocks per pass kind (tools/exp.py prints them)
 		long long passT0 = 0;
@@ -349,7 +225,12 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 				}
 				float u = (pxf + uniform01(r.x)) * invW; // trace.cu:190
 				float v = (pyf + uniform01(r.y)) * invH;
-				if (p.noJitter) pixelCentreUV(pxf, pyf, p.width, p.height, u, v); // the reference's primary-pass ray (parity aid; out of line: cold)
+#ifndef PTB_NO_PARITY_AIDS
+				// option "jitter" = 0 (parity aid): every sample through the pixel centre, u = (x + 0.5) / W with the IEEE division of the
+				// reference's primary pass - read from two small tables the host worked out (a division routine here, even out of
+				// line, cost the hot loop 2 %: its call constrains the register allocation of everything around it)
+				if (p.aids & kAidPixelCentre) { u = __ldg(p.centreU + __float2uint_rz(pxf)); v = __ldg(p.centreV + __float2uint_rz(pyf)); }
+#endif
 				rz = r.z; rw = r.w;
 				if constexpr (SHARE)
 				{
@@ -382,10 +263,14 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 			                                                                                SHARE && bounce == 0 ? nBeam : -1, stackColumn, SMEM ? nullptr : beamBoxes[SHARE ? threadIdx.x >> 5 : 0])
 			                          : closestHitWW<SMEM, COUNT, true, kHotExact, SSTACK>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? threadIdx.x >> 5 : 0],
 			                                                                               SHARE && bounce == 0 ? nBeam : -1, stackColumn, SMEM ? nullptr : beamBoxes[SHARE ? threadIdx.x >> 5 : 0]);
-			if (bounce == 0 && p.firstHitIndex != nullptr)
+#ifndef PTB_NO_PARITY_AIDS
+			if ((p.aids & kAidFirstHit) && bounce == 0)
+#else
+			if (false)
+#endif
 			{
 				// parity aid: what THIS kernel's traversal found for the camera ray (scene-order index, t), per pixel
-				p.firstHitIndex[pixel] = h.prim < 0 ? -1 : int32_t(__float_as_uint(sv.ld(sv.prims + h.prim * 4 + 3).y));
+				p.firstHitIndex[pixel] = h.prim < 0 ? -1 : int32_t(primSceneIndex(sv.ld(sv.prims + h.prim * 4 + 3)));
 				p.firstHitT[pixel] = h.prim < 0 ? 0.0f : h.t;
 			}
 
@@ -401,8 +286,10 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 				if (COUNT) ++misses;
 				if (p.scene.skybox != 0)
 				{
-					const float theta = fastAcos(rd.y), phi = fastAtan2(rd.z, rd.x);
-					const V3 sky = texLookupNI(p.scene.textures, p.scene.skybox, phi * (0.5f / PT_PI), theta * (1.0f / PT_PI));
+					// (both inlined: as calls - one copy each, shared with the texture-coordinate code - they cost the hot loop 3 %: two
+					// call / return pairs per miss, and the calling convention fixes registers around them)
+					const float theta = fastAcos(rd.y), phi = fastAtan2Inline(rd.z, rd.x);
+					const V3 sky = texLookup(p.scene.textures, p.scene.skybox, phi * (0.5f / PT_PI), theta * (1.0f / PT_PI));
 					if constexpr (SHARE) color = color + thr * sky; // the warp's partial sums take every contribution as it comes
 					else L = L + thr * sky;
 				}
@@ -428,7 +315,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 					const uint32_t tex = __float_as_uint(m2.x), mtype = __float_as_uint(m2.y);
 					if (tex != 0 && tex <= p.scene.texCount)
 					{
-						const V3 tap = texLookupNI(p.scene.textures, tex, s.u, s.v); // Material.inl:26-35
+						const V3 tap = texLookup(p.scene.textures, tex, s.u, s.v); // Material.inl:26-35
 						base = mk(fastPow(tap.x, 2.2f), fastPow(tap.y, 2.2f), fastPow(tap.z, 2.2f));
 					}
 					float rnd0, rnd1;
@@ -511,7 +398,7 @@ __global__ void __launch_bounds__(kThreads) primaryKernel(SceneDev scene, Camera
 		const V3 o = mk(cam.origin[0], cam.origin[1], cam.origin[2]);
 		const V3 d = cameraDir(cam, u, v);
 		const Hit h = closestHit<false, false>(sv, o, d, 0.001f, nv, pt);
-		hitIndex[i] = h.prim < 0 ? -1 : int32_t(__float_as_uint(__ldg(sv.prims + h.prim * 4 + 3).y));
+		hitIndex[i] = h.prim < 0 ? -1 : int32_t(primSceneIndex(__ldg(sv.prims + h.prim * 4 + 3)));
 		hitT[i] = h.prim < 0 ? 0.0f : h.t;
 	}
 }
@@ -529,7 +416,7 @@ __global__ void __launch_bounds__(kThreads) traceRaysKernel(SceneDev scene, uint
 		const V3 o = mk(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
 		const V3 d = mk(directions[3 * i], directions[3 * i + 1], directions[3 * i + 2]);
 		const Hit h = closestHit<false, false>(sv, o, d, tMin, nv, pt);
-		hitIndex[i] = h.prim < 0 ? -1 : int32_t(__float_as_uint(__ldg(sv.prims + h.prim * 4 + 3).y));
+		hitIndex[i] = h.prim < 0 ? -1 : int32_t(primSceneIndex(__ldg(sv.prims + h.prim * 4 + 3)));
 		hitT[i] = h.prim < 0 ? 0.0f : h.t;
 		if (hitNormal)
 		{
@@ -587,7 +474,7 @@ template <typename K>
 static int launchKernel(K kern, const RenderParams &p, const LaunchConfig &cfg, size_t smemBytes, cudaStream_t stream)
 {
 	// opt in whenever dynamic shared memory is used: the 48 KB default limit covers static + dynamic together, and the
-	// one-pixel-per-warp kernels carry ~20 KB of static shared memory (beam lists, sort counters)
+	// one-pixel-per-warp kernels carry ~20 KB of static shared memory (beam lists)
 	if (smemBytes > 0 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smemBytes)) != cudaSuccess)
 	{
 		cudaGetLastError();
@@ -605,7 +492,7 @@ static int launchKernel(K kern, const RenderParams &p, const LaunchConfig &cfg, 
 	return cudaPeekAtLastError() == cudaSuccess ? 1 : -1;
 }
 
-// static shared memory of the trace kernels (beam lists, per-warp pixel coordinates, sort counters, barrier; + the beam boxes of
+// static shared memory of the trace kernels (beam lists, per-warp pixel coordinates, barrier; + the beam boxes of
 // the global-memory instantiations) - an upper bound; launchKernel has the last word (occupancy query)
 constexpr size_t kStaticSmemBound = 36864;
 

@@ -37,12 +37,6 @@ struct RenderParams
 	uint32_t philoxKeys[20];
 	uint32_t maxBounces;
 	uint32_t regenLow = 1; // one-pixel-per-warp kernel: idle lanes wait until this many can start new samples together
-	// one-pixel-per-warp kernel: the samples of a pixel are handed out in the order of their first scattering direction
-	// (sortSamples, trace_kernels.cu).  sortScratch = sortStride x 4 bytes per warp of the grid; 0 = samples in index order
-	uint16_t *sortScratch = nullptr;
-	uint32_t sortStride = 0;
-	uint32_t sortIgnore = 0; // timing aid: sort, then hand the samples out in index order all the same
-	uint32_t sortBitsA = 4, sortBitsB = 2; // bins of the first / second random (2^(A+B) bins, 32..256)
 	uint32_t beam = 0;     // one-pixel-per-warp kernel: camera rays take their leaves from the pixel's beam list (trace_device.cuh)
 	// First-bounce stratification (one-pixel-per-warp kernels).  The launch's first strataPer << (strataBitsA + strataBitsB)
 	// samples of a pixel (local index m) take the first scattering direction's two randoms from cell m / strataPer of a
@@ -52,13 +46,18 @@ struct RenderParams
 	// or second Philox evaluation.  strataPer = 0: off.
 	uint32_t strataPer = 0, strataBitsA = 0, strataBitsB = 0;
 	float strataInvPer = 0.0f;
-	uint32_t noJitter = 0;          // parity aid: every sample through the pixel centre (u = (x + 0.5) / W, like the reference's primary pass)
+	// parity aid (option "jitter" = 0): every sample through the pixel centre; centreU[x] = (x + 0.5f) / W, centreV[y] = (y + 0.5f) / H with
+	// IEEE division, like the reference's primary pass - tables made by the host (pt_render); nullptr = jittered samples
+	const float *centreU = nullptr, *centreV = nullptr;
+	uint32_t aids = 0;              // kAid* bits: which parity aids are on (ONE warp-uniform test per site in the kernel)
 	int32_t *firstHitIndex = nullptr; // parity aid: scene index (-1: miss) and t of the camera ray's closest hit, per pixel, written by
 	float *firstHitT = nullptr;       // the render kernel itself (with noJitter every sample of a pixel writes the same values)
 	float alpha = 1.0f;             // what the kernel writes to the accumulation buffer's fourth channel (trace.cu:198 writes 1); a multi-GPU
 	                                // sample partition lets only its first device write 1, so that the summed alpha is 1 as on one GPU
 	uint32_t stackOffset = 0;       // SSTACK kernels: byte offset of the shared-memory traversal stack in dynamic shared memory
 };
+
+constexpr uint32_t kAidPixelCentre = 1u, kAidFirstHit = 2u;
 
 struct LaunchConfig
 {
@@ -69,8 +68,6 @@ struct LaunchConfig
 	                     //  5: + leaf parking; 8: one pixel per WARP (lanes = samples), while-while; 9/10: its other traversals;
 	                     //  12: 8 with separate passes for camera rays and scattered rays)
 	int regenLow = 0;    // see RenderParams::regenLow (0 = default)
-	int sortBitsA = 0, sortBitsB = -1; // 0 / -1 = defaults
-	int sortSamples = 0; // order a pixel's samples by first scattering direction (round 1; superseded by `stratify`): 1 on, 0 off (default)
 	int beam = -1;       // pixel beams for the camera rays of the one-pixel-per-warp kernel: 1 on, 0 off, -1 = on from 128 spp
 	int stratify = -1;   // first-bounce stratification (RenderParams::strataPer): 1 on, 0 off, -1 = on from 128 spp (one-pixel-per-warp kernels)
 	int strataK = 0;     // experiments: log2 of the cell count (0 = the rule of pt_render: at least 32 samples per cell, at most 128 cells)

@@ -122,7 +122,7 @@ void emu_primary(void *p, const pt_camera_desc *cd, uint32_t width, uint32_t hei
 			const V3 o = mk(cam.origin[0], cam.origin[1], cam.origin[2]);
 			const V3 d = cameraDir(cam, u, v);
 			const Hit h = closestHit<false, true>(sv, o, d, 0.001f, nv, pt);
-			hitIndex[i] = h.prim < 0 ? -1 : int32_t(__float_as_uint(sv.prims[h.prim * 4 + 3].y));
+			hitIndex[i] = h.prim < 0 ? -1 : int32_t(primSceneIndex(sv.prims[h.prim * 4 + 3]));
 			hitT[i] = h.prim < 0 ? 0.0f : h.t;
 			nvTot += nv; ptTot += pt;
 		}
@@ -155,7 +155,7 @@ void emu_first_hit(void *p, const pt_camera_desc *cd, uint32_t width, uint32_t h
 			const V3 o = mk(cam.origin[0], cam.origin[1], cam.origin[2]);
 			const V3 d = cameraDir<2>(cam, u, v);
 			const Hit h = closestHitWW<false, true, false, kHotExact>(sv, o, d, 0.001f, nv, pt, beam, nBeam, 0, boxes);
-			hitIndex[i] = h.prim < 0 ? -1 : int32_t(__float_as_uint(sv.prims[h.prim * 4 + 3].y));
+			hitIndex[i] = h.prim < 0 ? -1 : int32_t(primSceneIndex(sv.prims[h.prim * 4 + 3]));
 			hitT[i] = h.prim < 0 ? 0.0f : h.t;
 		}
 }
@@ -172,7 +172,7 @@ void emu_trace_rays(void *p, size_t n, const float *origins, const float *direct
 		const V3 o = mk(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]);
 		const V3 d = mk(directions[3 * i], directions[3 * i + 1], directions[3 * i + 2]);
 		const Hit h = closestHit<false, false>(sv, o, d, tMin, nv, pt);
-		hitIndex[i] = h.prim < 0 ? -1 : int32_t(__float_as_uint(sv.prims[h.prim * 4 + 3].y));
+		hitIndex[i] = h.prim < 0 ? -1 : int32_t(primSceneIndex(sv.prims[h.prim * 4 + 3]));
 		hitT[i] = h.prim < 0 ? 0.0f : h.t;
 		if (hitNormal)
 		{

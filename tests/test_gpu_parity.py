@@ -292,29 +292,26 @@ def test_textures_and_skybox():
     assert (rel.max(-1) > 2e-3).mean() < 0.03 and abs(a[..., :3].mean() / b[..., :3].mean() - 1) < 2e-3
 
 
-def test_sample_order_changes_nothing_but_the_order():
-    """long renders hand a pixel's samples to the lanes in the order of their first scattering direction (sortSamples):
-    the same Philox counters, so the same paths and ray count; the image differs by float summation order only and is
-    the same from run to run; also with a sample partition (offset / stride) and when accumulating onto an earlier render"""
-    def run(sort, **opts):
+def test_ragged_long_renders_are_deterministic():
+    """the one-pixel-per-warp kernel with plain Philox draws (stratification off): sample counts that are not a multiple of
+    the warp size, a second call accumulating onto the first, a sample partition (offset / stride) - the same bits from run
+    to run, the same ray count however the lanes were filled"""
+    def run(**opts):
         with pt.Pathtracer(160, 90) as P:
             cam = P.loadSceneFile(f"{pt.ASSETS}/scenes/generated_scene.json", cwd=pt.ASSETS)
-            P.setOption("stratify", 0)  # the sort is the alternative to the stratification: plain Philox draws, ordered
-            P.setOption("sort_samples", sort)
+            P.setOption("stratify", 0)
             for k, v in opts.items():
                 P.setOption(k, v)
-            P.render(cam, 1056, True)   # not a multiple of 32 on purpose... 1056 = 33 x 32; and a ragged second call
-            P.render(cam, 1031, False)
+            P.render(cam, 1056, True)
+            P.render(cam, 1031, False)  # ragged second call
             return P.getHDRMean(), P.stats().rays
-    a, ra = run(0)
-    b, rb = run(1)
-    c, rc = run(1)
-    assert ra == rb == rc and np.array_equal(bits(b), bits(c))
-    assert not np.array_equal(bits(a), bits(b)) and np.allclose(a, b, rtol=3e-5, atol=1e-7)
-    a2, r2 = run(0, sample_offset=3, sample_stride=4)
-    b2, r3 = run(1, sample_offset=3, sample_stride=4)
-    assert r2 == r3 and np.allclose(a2, b2, rtol=3e-5, atol=1e-7) and not np.allclose(a, a2, rtol=1e-3)
-    assert np.allclose(run(1, sort_bits_a=5, sort_bits_b=2)[0], a, rtol=3e-5, atol=1e-7)
+    a, ra = run()
+    b, rb = run()
+    c, rc = run(regen_low=8)  # lanes refilled in smaller groups: other summation order, same paths
+    assert ra == rb == rc and np.array_equal(bits(a), bits(b)) and np.allclose(a, c, rtol=3e-5, atol=1e-7)
+    a2, r2 = run(sample_offset=3, sample_stride=4)
+    b2, r3 = run(sample_offset=3, sample_stride=4)
+    assert r2 == r3 and np.array_equal(bits(a2), bits(b2)) and not np.allclose(a, a2, rtol=1e-3)
 
 
 def test_first_bounce_stratification_is_unbiased_and_deterministic():

@@ -193,19 +193,30 @@ def _validate_bvh(objs, max_leaf=4):
     boxes = np.array([O.object_info(i)[1] for i in range(len(objs))])
     nf = nodes.view(np.float32)
     seen = np.zeros(len(objs), int)
-    assert sorted(prims[:, 13].tolist()) == list(range(len(objs)))  # sceneIndex is a permutation
+    # the fourth quad of a primitive record (pt_types.h): quadric coefficients B, H, J as floats, then one packed word
+    packed = prims[:, 15].astype(np.uint32)
+    scene_of, type_of = (packed & 0xffffff).astype(np.int64), ((packed >> 24) & 7).astype(np.int64)
+    assert sorted(scene_of.tolist()) == list(range(len(objs)))  # sceneIndex is a permutation
+    coef = prims[:, 12:15].copy().view(np.float32)
+    for k in range(len(objs)):
+        t = int(objs[int(scene_of[k])].type)
+        assert type_of[k] == t
+        want = {0: (1, 0, -1), 1: (0, 0, -1), 3: (-1, 0, 0), 4: (0, -1, 0)}.get(t, (0, 0, 0))  # sphere, cylinder, cone, paraboloid (Hittable.inl:151,176,242,273)
+        assert tuple(coef[k]) == want
+        bits = int(packed[k]) >> 27
+        assert bits == (int(objs[int(scene_of[k])].material.texture != 0) | (2 if t in (2, 5) else 0) | (4 if t == 6 else 0) | (8 if t == 2 else 0) | (16 if t == 0 else 0))
 
     def walk(ref, depth):
         if ref < 0:
             u = ref & 0xffffffff
             first, count, typ = u & 0xffffff, (u >> 24) & 15, (u >> 28) & 7
             assert 1 <= count <= max(max_leaf, 1)
-            assert typ == prims[first, 12]
-            cls = [1 if prims[k, 12] in (2, 5) else (2 if prims[k, 12] == 6 else 0) for k in range(first, first + count)]
+            assert typ == type_of[first]
+            cls = [1 if type_of[k] in (2, 5) else (2 if type_of[k] == 6 else 0) for k in range(first, first + count)]
             assert cls == sorted(cls), "leaf primitives are ordered quadrics, flat shapes, cubes"
             b = np.array([[np.inf] * 3, [-np.inf] * 3])
             for k in range(first, first + count):
-                s = prims[k, 13]
+                s = scene_of[k]
                 seen[s] += 1
                 b[0] = np.minimum(b[0], boxes[s][:3])
                 b[1] = np.maximum(b[1], boxes[s][3:])
@@ -233,9 +244,9 @@ def _validate_bvh(objs, max_leaf=4):
     assert G <= 8 and G < len(objs)
     scene_area = _area(np.array([boxes[:, :3].min(0), boxes[:, 3:].max(0)]))
     for k in range(len(objs)):
-        a = _area(np.array([boxes[prims[k, 13]][:3], boxes[prims[k, 13]][3:]]))
+        a = _area(np.array([boxes[scene_of[k]][:3], boxes[scene_of[k]][3:]]))
         if k < G:
-            seen[prims[k, 13]] += 1
+            seen[scene_of[k]] += 1
             assert a >= 0.25 * scene_area * (1 - 1e-5)
         elif G < 8 and G < len(objs) - 1:
             assert a < 0.25 * scene_area * (1 + 1e-5), "a scene-spanning primitive was left in the tree"

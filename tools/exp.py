@@ -20,7 +20,9 @@ with pt.Pathtracer(W, H) as P:
     P.render(cam, 8, True)
     best = min((P.render(cam, spp, True), P.getTiming())[1] for _ in range(3))
     st = P.stats()
-    print(json.dumps({"scene": scene, "variant": variant, "spp": spp, "opts": sys.argv[4:], "ms": round(best, 3), "Mrays_s": round(st.rays / best / 1e3, 1),
+    import zlib
+    crc = zlib.crc32(P.getHDRMean().tobytes())
+    print(json.dumps({"crc": crc, "scene": scene, "variant": variant, "spp": spp, "opts": sys.argv[4:], "ms": round(best, 3), "Mrays_s": round(st.rays / best / 1e3, 1),
                       "rays_per_sample": round(st.rays / st.samples, 3), "nodes_per_ray": round(st.node_visits / st.rays, 2), "prims_per_ray": round(st.prim_tests / st.rays, 2),
                       "bvh_nodes": st.bvh_nodes, "smem": st.scene_in_smem}), flush=True)
     import ctypes as C
