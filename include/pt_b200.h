@@ -198,6 +198,11 @@ const float *pt_get_hdr_sum(pt_context *ctx);
  *  "first_hit"       1: pt_render also records, per pixel, the scene index and t of the closest hit of the camera ray AS FOUND BY
  *                    THE RENDER KERNEL ITSELF (pt_get_first_hit); with "jitter" = 0 this is the primary-pass gate on the
  *                    production traversal (beams, MUFU reciprocals and all)
+ *  "env_is"          1: every scattering vertex also draws one direction from the sky's importance distribution
+ *                    (pt_env_distribution) and the sky light reaching it is estimated by multiple importance sampling (balance
+ *                    heuristic) of that draw and the BSDF's own.  The same integral as the reference's estimator (paths of at
+ *                    most max_bounces segments, sky light through a miss) - the image converges to the same picture, with less
+ *                    variance per sample under a sky with a sun; one more ray per vertex.  Default 0 (trace.cu:115-134).
  *  "tex_unit"        1 (default): texture taps through CUDA texture objects, as the reference (Pathtracer.cpp:259-288);
  *                    0: fp32 bilinear filter in software over the packed texels */
 int pt_set_option(pt_context *ctx, const char *key, double value);
@@ -241,6 +246,14 @@ int pt_write_hdr(const char *path, uint32_t width, uint32_t height, const float 
 /* decoders used by pt_load_texture (stbi_load / stbi_loadf replacement).  Caller frees with pt_free. */
 int pt_read_image(const char *path, uint32_t *width, uint32_t *height, int *is_hdr, void **rgba);
 void pt_free(void *p);
+
+/* The importance distribution option "env_is" samples the sky with (no counterpart in the reference, which evaluates the sky only
+ * where a path misses, kernels/trace.cu:115-134): a grid of cols x rows cells (at most 512 x 256) over the equirectangular map
+ * `rgba` (width x height, float RGBA when is_hdr, else RGBA8), cell weight = sum over its texels of luminance x sin(theta).
+ * alias: 2 words per cell (float bits of the acceptance threshold, alias cell) - one table over all cells; density: per cell
+ * P(cell) x cells / (2 pi^2), so that the solid-angle pdf of a direction in the cell is density / sin(theta).  Host only.
+ * Call with alias = density = NULL for the grid size; returns the cell count or a negative error. */
+int pt_env_distribution(uint32_t width, uint32_t height, int is_hdr, const void *rgba, uint32_t *cols, uint32_t *rows, uint32_t *alias, float *density);
 
 const char *pt_last_error(void);
 const char *pt_version(void);

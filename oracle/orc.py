@@ -73,6 +73,32 @@ class Oracle:
     def set_skybox(self, h):
         self.L.orc_set_skybox(self.s, h)
 
+    def set_env_is(self, on):
+        """the product's option "env_is" (not the reference): sky importance sampling + multiple importance sampling"""
+        self.L.orc_set_env_is.argtypes = [C.c_void_p, C.c_int]
+        self.L.orc_set_env_is(self.s, int(on))
+
+    def env_tables(self):
+        """(cols, rows, q, alias, density) of the sky distribution built by set_env_is(1)"""
+        self.L.orc_env_tables.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+        self.L.orc_env_tables.restype = C.c_uint32
+        cols, rows = C.c_uint32(), C.c_uint32()
+        n = self.L.orc_env_tables(self.s, C.byref(cols), C.byref(rows), None, None, None)
+        q, alias, dens = np.zeros(n, np.float32), np.zeros(n, np.uint32), np.zeros(n, np.float32)
+        self.L.orc_env_tables(self.s, None, None, _p(q), _p(alias), _p(dens))
+        return cols.value, rows.value, q, alias, dens
+
+    def env_sample(self, r):
+        """r: (n, 3) uint32 random words -> (n, 6): direction, u, v, pdf"""
+        self.L.orc_env_sample.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
+        r = np.ascontiguousarray(r, np.uint32)
+        out = np.zeros((r.shape[0], 6), np.float32)
+        row = np.zeros(6, np.float32)
+        for i in range(r.shape[0]):
+            self.L.orc_env_sample(self.s, int(r[i, 0]), int(r[i, 1]), int(r[i, 2]), _p(row))
+            out[i] = row
+        return out
+
     def bvh_info(self):
         n, d, v = C.c_uint32(), C.c_uint32(), C.c_int32()
         self.L.orc_bvh_info(self.s, C.byref(n), C.byref(d), C.byref(v))

@@ -47,6 +47,8 @@ struct orc_scene
 	obj_t *sceneObjs; /* scene order */
 	node_t *nodes; uint32_t nodeCount, nodeCap;
 	tex_t tex[64]; uint32_t texCount; uint32_t skybox;
+	/* NOT THE REFERENCE: importance distribution of the sky (option "env_is" of the product, csrc/env_sampling.h) */
+	int envIS; uint32_t envCols, envRows; float *envQ; uint32_t *envAlias; float *envDensity;
 };
 
 /* ---- vec3.inl ------------------------------------------------------------------------------------------ */
@@ -563,6 +565,34 @@ static inline v3 lerp3(v3 x, v3 y, float a) { return vadd(vscale(1.0f - a, x), v
 
 /* Material::sample  Material.inl:20-60 (+ sampleLambert :67-72, sampleGGX :74-99, sampleLambertGGX :101-144).
  * Returns attenuation; *pdf, *scatteredDir (world).  baseColor already texture-resolved by the caller. */
+/* NOT THE REFERENCE (a helper of the "env_is" estimator): attenuation and pdf of Material::sample for a GIVEN tangent-space
+ * direction - the same expressions as in materialSample below (Material.inl:67-72, :89-98, :124-143), which are functions of the
+ * view vector and the scattered direction alone. */
+static v3 materialEval(uint32_t mtype, v3 baseColor, float roughness, float metalness, v3 Vv, v3 sdir, float *pdf)
+{
+	v3 att = V(0.0f, 0.0f, 0.0f);
+	*pdf = 0.0f;
+	if (mtype == PT_LAMBERT) { *pdf = sdir.z / PI_F; att = vscale(1.0f / PI_F, baseColor); }
+	else if (mtype == PT_GGX || mtype == PT_LAMBERT_GGX)
+	{
+		const float a = roughness * roughness, a2 = a * a;
+		if (sdir.z < 0.0f) { *pdf = 1.0f; return att; }
+		const float NdotV = fabsf(Vv.z) + 1e-5f;
+		const v3 H = vnorm(vadd(Vv, sdir));
+		const float VdotH = clampf(vdot(Vv, H), 0.0f, 1.0f), NdotH = clampf(H.z, 0.0f, 1.0f), NdotL = clampf(sdir.z, 0.0f, 1.0f);
+		const v3 F0 = lerp3(V(0.04f, 0.04f, 0.04f), baseColor, metalness);
+		const v3 kS = Specular_GGX(F0, NdotV, NdotL, NdotH, VdotH, a2);
+		if (mtype == PT_GGX) { *pdf = importanceSampleGGXVNDFPdf(H, Vv, a); att = kS; }
+		else
+		{
+			const float cosinePdf = sdir.z / PI_F, ggxPdf = importanceSampleGGXVNDFPdf(H, Vv, a);
+			*pdf = (ggxPdf + cosinePdf) * 0.5f;
+			att = vadd(vscale(1.0f - metalness, vscale(1.0f / PI_F, baseColor)), kS);
+		}
+	}
+	return att;
+}
+
 static v3 materialSample(uint32_t mtype, v3 baseColor, float roughness, float metalness, v3 N, v3 inDir, float rnd0, float rnd1, v3 *scattered, float *pdf)
 {
 	const v3 Vv = worldToTangent(N, vneg(inDir));
@@ -614,10 +644,96 @@ static v3 resolveBaseColor(const orc_scene *s, const obj_t *o, float u, float v)
 	return bc;
 }
 
+/* ---- NOT THE REFERENCE: the sky's importance distribution (the product's option "env_is"; csrc/env_sampling.h states the
+ * estimator).  Restated here so that the CUDA path can be checked path for path: a grid of at most 512 x 256 cells over the
+ * equirectangular map, weight = sum over the cell's texels of luminance x sin(theta) plus a floor of 1e-4 of the mean, one alias
+ * table over all cells (Vose, work lists filled in index order, used as stacks), density = P(cell) cells / (2 pi^2). ---- */
+static void envBuild(orc_scene *s)
+{
+	free(s->envQ); free(s->envAlias); free(s->envDensity);
+	s->envQ = NULL; s->envAlias = NULL; s->envDensity = NULL; s->envCols = s->envRows = 0;
+	if (s->skybox == 0 || s->skybox > s->texCount) return;
+	const tex_t *t = &s->tex[s->skybox - 1];
+	const uint32_t bw = (t->w + 511u) / 512u, bh = (t->h + 255u) / 256u;
+	const uint32_t cols = (t->w + bw - 1u) / bw, rows = (t->h + bh - 1u) / bh;
+	const size_t n = (size_t)cols * rows;
+	double *w = (double *)calloc(n, sizeof(double)), *scaled = (double *)malloc(n * sizeof(double));
+	const double pi = 3.14159265358979323846;
+	for (uint32_t y = 0; y < t->h; ++y)
+	{
+		const double sinTheta = sin(pi * ((double)y + 0.5) / (double)t->h);
+		for (uint32_t x = 0; x < t->w; ++x)
+		{
+			const size_t k = ((size_t)y * t->w + x) * 4;
+			double r, g, b;
+			if (t->hdr) { r = t->f[k]; g = t->f[k + 1]; b = t->f[k + 2]; }
+			else { r = t->b[k] / 255.0; g = t->b[k + 1] / 255.0; b = t->b[k + 2] / 255.0; }
+			double lum = 0.2126 * r + 0.7152 * g + 0.0722 * b;
+			if (!(lum > 0.0) || !(lum < 1e30)) lum = 0.0;
+			w[(size_t)(y / bh) * cols + x / bw] += lum * sinTheta;
+		}
+	}
+	double total = 0.0;
+	for (size_t i = 0; i < n; ++i) total += w[i];
+	if (!(total > 0.0)) { for (size_t i = 0; i < n; ++i) w[i] = 1.0; total = (double)n; }
+	const double floorW = 1e-4 * total / (double)n;
+	double total2 = 0.0;
+	for (size_t i = 0; i < n; ++i) { w[i] += floorW; total2 += w[i]; }
+	s->envQ = (float *)malloc(n * sizeof(float)); s->envAlias = (uint32_t *)malloc(n * sizeof(uint32_t)); s->envDensity = (float *)malloc(n * sizeof(float));
+	for (size_t i = 0; i < n; ++i)
+	{
+		const double p = w[i] / total2;
+		s->envDensity[i] = (float)(p * (double)n / (2.0 * pi * pi));
+		scaled[i] = p * (double)n;
+	}
+	uint32_t *small = (uint32_t *)malloc(n * sizeof(uint32_t)), *large = (uint32_t *)malloc(n * sizeof(uint32_t));
+	size_t ns = 0, nl = 0;
+	for (size_t i = 0; i < n; ++i) { if (scaled[i] < 1.0) small[ns++] = (uint32_t)i; else large[nl++] = (uint32_t)i; }
+#define ENV_PUT(cell, q, other) do { double q_ = (q); s->envQ[cell] = (float)(q_ < 0.0 ? 0.0 : (q_ > 1.0 ? 1.0 : q_)); s->envAlias[cell] = (other); } while (0)
+	while (ns > 0 && nl > 0)
+	{
+		const uint32_t sm = small[--ns], lg = large[nl - 1];
+		ENV_PUT(sm, scaled[sm], lg);
+		scaled[lg] = (scaled[lg] + scaled[sm]) - 1.0;
+		if (scaled[lg] < 1.0) { --nl; small[ns++] = lg; }
+	}
+	for (size_t i = 0; i < nl; ++i) ENV_PUT(large[i], 1.0, large[i]);
+	for (size_t i = 0; i < ns; ++i) ENV_PUT(small[i], 1.0, small[i]);
+#undef ENV_PUT
+	free(small); free(large); free(w); free(scaled);
+	s->envCols = cols; s->envRows = rows;
+}
+/* one direction ~ the distribution from three random words (cell by the alias table with integer arithmetic, position inside the
+ * cell from the other two), its lookup coordinates and solid-angle pdf */
+static v3 envSample(const orc_scene *s, uint32_t r0, uint32_t r1, uint32_t r2, float *u, float *v, float *pdf)
+{
+	const uint32_t cells = s->envCols * s->envRows;
+	const uint64_t x = (uint64_t)r0 * cells;
+	const uint32_t i = (uint32_t)(x >> 32);
+	const float frac = (float)(uint32_t)x * 2.3283064365386963e-10f;
+	const uint32_t cell = frac < s->envQ[i] ? i : s->envAlias[i];
+	const uint32_t row = cell / s->envCols, col = cell - row * s->envCols;
+	*u = ((float)col + orc_uniform(r1)) * (1.0f / (float)s->envCols);
+	*v = ((float)row + orc_uniform(r2)) * (1.0f / (float)s->envRows);
+	const float phi = 2.0f * PI_F * *u, theta = PI_F * *v;
+	const float st = sinf(theta), ct = cosf(theta);
+	*pdf = s->envDensity[cell] * (1.0f / fmaxf(st, 1e-6f));
+	return V(st * cosf(phi), ct, st * sinf(phi));
+}
+static float envPdf(const orc_scene *s, float u, float v, float dirY)
+{
+	const float uw = u - floorf(u);
+	uint32_t col = (uint32_t)(uw * (float)s->envCols), row = (uint32_t)(fmaxf(v, 0.0f) * (float)s->envRows);
+	if (col > s->envCols - 1u) col = s->envCols - 1u;
+	if (row > s->envRows - 1u) row = s->envRows - 1u;
+	return s->envDensity[row * s->envCols + col] * (1.0f / sqrtf(fmaxf(1.0f - dirY * dirY, 1e-12f)));
+}
+
 /* getColor  kernels/trace.cu:101-156 */
 static v3 getColor(const orc_scene *s, ray_t ray, uint32_t pixel, uint32_t sample, uint32_t k0, uint32_t k1, const uint32_t rng0[4], int maxBounces, uint64_t *rays)
 {
 	v3 throughput = V(1.0f, 1.0f, 1.0f), L = V(0.0f, 0.0f, 0.0f);
+	float lastPdf = 0.0f;
 	uint32_t rng[4] = { rng0[0], rng0[1], rng0[2], rng0[3] };
 	for (int it = 0; it < maxBounces; ++it)
 	{
@@ -633,6 +749,13 @@ static v3 getColor(const orc_scene *s, ray_t ray, uint32_t pixel, uint32_t sampl
 				texLookup(&s->tex[s->skybox - 1], u, v, tap);
 				c = V(tap[0], tap[1], tap[2]);
 			}
+			if (s->envIS && it > 0 && s->skybox != 0 && s->skybox <= s->texCount)
+			{
+				/* NOT THE REFERENCE: balance-heuristic weight of a BSDF-sampled direction that reached the sky */
+				const float theta = acosf(ray.d.y), phi = atan2f(ray.d.z, ray.d.x);
+				const float pe = envPdf(s, phi / (2.0f * PI_F), theta / PI_F, ray.d.y);
+				c = vscale(lastPdf / (lastPdf + pe), c);
+			}
 			L = vadd(L, vmul(throughput, c));
 			break;
 		}
@@ -647,7 +770,31 @@ static v3 getColor(const orc_scene *s, ray_t ray, uint32_t pixel, uint32_t sampl
 			rnd0 = orc_uniform(rng[(it & 1) ? 0 : 2]); rnd1 = orc_uniform(rng[(it & 1) ? 1 : 3]);
 		}
 		v3 sdir; float pdf;
-		v3 att = materialSample(o->mtype, resolveBaseColor(s, o, rec.u, rec.v), o->roughness, o->metalness, rec.n, ray.d, rnd0, rnd1, &sdir, &pdf);
+		const v3 base = resolveBaseColor(s, o, rec.u, rec.v);
+		if (s->envIS && s->skybox != 0 && s->skybox <= s->texCount && it + 1 < maxBounces)
+		{
+			/* NOT THE REFERENCE: one direction from the sky's distribution per scattering vertex (Philox counter word 3 = 1,
+			 * slot = bounce), weighted against the BSDF's pdf for the same direction; shadow ray with the path's own tMin */
+			uint32_t q[4];
+			orc_philox(pixel, sample, (uint32_t)it, 1, k0, k1, q);
+			float lu, lv, pe;
+			const v3 wl = envSample(s, q[0], q[1], q[2], &lu, &lv, &pe);
+			const v3 Vv = worldToTangent(rec.n, vneg(ray.d)), sl = worldToTangent(rec.n, wl);
+			float pbL;
+			const v3 attL = materialEval(o->mtype, base, o->roughness, o->metalness, Vv, sl, &pbL);
+			if (sl.z > 0.0f && !((attL.x == 0.0f && attL.y == 0.0f && attL.z == 0.0f) || pbL == 0.0f))
+			{
+				float tap[4];
+				texLookup(&s->tex[s->skybox - 1], lu, lv, tap);
+				ray_t sh; sh.o = rec.p; sh.d = wl;
+				hit_t srec; uint32_t selem;
+				++*rays;
+				if (!hitBVH(s, sh, 0.001f, FLT_MAX, &srec, &selem, NULL, NULL))
+					L = vadd(L, vmul(vmul(throughput, vscale(sl.z / (pe + pbL), attL)), V(tap[0], tap[1], tap[2])));
+			}
+		}
+		v3 att = materialSample(o->mtype, base, o->roughness, o->metalness, rec.n, ray.d, rnd0, rnd1, &sdir, &pdf);
+		lastPdf = pdf;
 		if ((att.x == 0.0f && att.y == 0.0f && att.z == 0.0f) || pdf == 0.0f) break;
 		/* throughput *= attenuation * abs(dot(scattered.m_dir, rec.m_normal)) / pdf   (trace.cu:150):
 		 * (att * |dot|) / pdf = (1/pdf) * (|dot| * att) */
@@ -680,6 +827,7 @@ void orc_scene_destroy(orc_scene *s)
 {
 	if (!s) return;
 	for (uint32_t i = 0; i < s->texCount; ++i) { free(s->tex[i].f); free(s->tex[i].b); }
+	free(s->envQ); free(s->envAlias); free(s->envDensity);
 	free(s->objs); free(s->toScene); free(s->sceneObjs); free(s->nodes); free(s);
 }
 uint32_t orc_add_texture(orc_scene *s, uint32_t w, uint32_t h, int is_hdr, const void *rgba)
@@ -692,7 +840,27 @@ uint32_t orc_add_texture(orc_scene *s, uint32_t w, uint32_t h, int is_hdr, const
 	if (is_hdr) t->f = (float *)p; else t->b = (uint8_t *)p;
 	return ++s->texCount;
 }
-void orc_set_skybox(orc_scene *s, uint32_t handle) { s->skybox = handle; }
+void orc_set_skybox(orc_scene *s, uint32_t handle) { s->skybox = handle; if (s->envIS) envBuild(s); }
+/* NOT THE REFERENCE: switch the "env_is" estimator on / off (builds the distribution of the current sky) */
+void orc_set_env_is(orc_scene *s, int on) { s->envIS = on != 0; if (s->envIS) envBuild(s); }
+/* the tables, for tests: returns the cell count (0 = none); q / alias / density may be NULL */
+uint32_t orc_env_tables(const orc_scene *s, uint32_t *cols, uint32_t *rows, float *q, uint32_t *alias, float *density)
+{
+	const uint32_t n = s->envCols * s->envRows;
+	if (cols) *cols = s->envCols;
+	if (rows) *rows = s->envRows;
+	if (n && q) memcpy(q, s->envQ, n * sizeof(float));
+	if (n && alias) memcpy(alias, s->envAlias, n * sizeof(uint32_t));
+	if (n && density) memcpy(density, s->envDensity, n * sizeof(float));
+	return n;
+}
+/* one sample of the distribution (tests): out6 = direction, u, v, pdf */
+void orc_env_sample(const orc_scene *s, uint32_t r0, uint32_t r1, uint32_t r2, float *out6)
+{
+	float u, v, pdf;
+	const v3 d = envSample(s, r0, r1, r2, &u, &v, &pdf);
+	out6[0] = d.x; out6[1] = d.y; out6[2] = d.z; out6[3] = u; out6[4] = v; out6[5] = pdf;
+}
 void orc_bvh_info(const orc_scene *s, uint32_t *nodes, uint32_t *depth, int32_t *valid)
 {
 	*nodes = s->nodeCount; *depth = s->nodeCount ? bvhDepth(s, 0) : 0;

@@ -14,6 +14,10 @@ void orc_scene_destroy(orc_scene *s);
 /* textures: 1-based handles in load order, like Pathtracer::loadTexture */
 uint32_t orc_add_texture(orc_scene *s, uint32_t w, uint32_t h, int is_hdr, const void *rgba);
 void orc_set_skybox(orc_scene *s, uint32_t handle);
+/* NOT THE REFERENCE: the product's "env_is" estimator (csrc/env_sampling.h), restated so that the CUDA path can be checked path for path */
+void orc_set_env_is(orc_scene *s, int on);
+uint32_t orc_env_tables(const orc_scene *s, uint32_t *cols, uint32_t *rows, float *q, uint32_t *alias, float *density);
+void orc_env_sample(const orc_scene *s, uint32_t r0, uint32_t r1, uint32_t r2, float *out6);
 void orc_bvh_info(const orc_scene *s, uint32_t *nodes, uint32_t *depth, int32_t *valid);
 /* per object: 12 floats world->local rows, 6 floats AABB (min, max) */
 void orc_object_info(const orc_scene *s, size_t i, float *rows12, float *aabb6);

@@ -3,6 +3,7 @@
 // no CPU fallback (pt_create fails without a device).
 #include "../../include/pt_b200.h"
 #include "image_io.h"
+#include "env_sampling.h"
 #include "scene_compile.h"
 #include "scene_loader.h"
 #include "trace_kernels.h"
@@ -44,6 +45,12 @@ struct pt_context
 	int32_t *firstHitIndex = nullptr; // option "first_hit": the render kernel's own first-hit (index, t) per pixel (parity aid)
 	float *firstHitT = nullptr;
 	bool firstHit = false, noJitter = false;
+	// option "env_is": the sky's importance distribution (env_sampling.h), built for texture handle envHandle on first use
+	bool envIS = false;
+	uint32_t envHandle = 0;
+	void *envAlias = nullptr;
+	float *envDensity = nullptr;
+	uint32_t envCols = 0, envRows = 0;
 	float *centreUV = nullptr; // option "jitter" = 0: pixel-centre coordinates (RenderParams::centreU / centreV), made on first use
 	// scene
 	float4 *sceneBlob = nullptr;
@@ -263,9 +270,10 @@ void pt_destroy(pt_context *c)
 	if (c->firstHitIndex) cudaFree(c->firstHitIndex);
 	if (c->firstHitT) cudaFree(c->firstHitT);
 	if (c->centreUV) cudaFree(c->centreUV);
+	if (c->envAlias) cudaFree(c->envAlias);
+	if (c->envDensity) cudaFree(c->envDensity);
 	if (c->texDev) cudaFree(c->texDev);
-	if (c->sceneBlob) cudaFree(c->sceneBlob);
-	if (c->mats) cudaFree(c->mats);
+	if (c->sceneBlob) cudaFree(c->sceneBlob); // (the material table lives in the same allocation)
 	for (void *p : c->texMem) cudaFree(p);
 	for (cudaTextureObject_t o : c->texObjects) cudaDestroyTextureObject(o);
 	for (cudaArray_t a : c->texArrays) cudaFreeArray(a);
@@ -281,13 +289,14 @@ static int uploadScene(pt_context *c, const CompiledScene &cs)
 	CK(cudaSetDevice(c->device));
 	CK(cudaStreamSynchronize(c->stream));
 	if (c->sceneBlob) { CK(cudaFree(c->sceneBlob)); c->sceneBlob = nullptr; }
-	if (c->mats) { CK(cudaFree(c->mats)); c->mats = nullptr; }
-	const size_t nodeBytes = cs.nodes.size() * sizeof(Node), primBytes = cs.prims.size() * sizeof(Prim);
-	CK(cudaMalloc(&c->sceneBlob, nodeBytes + primBytes));
-	CK(cudaMalloc(&c->mats, cs.mats.size() * sizeof(Mat)));
+	c->mats = nullptr;
+	// one allocation, nodes | primitives | materials: a scene that fits is staged in shared memory whole, by one bulk copy
+	const size_t nodeBytes = cs.nodes.size() * sizeof(Node), primBytes = cs.prims.size() * sizeof(Prim), matBytes = cs.mats.size() * sizeof(Mat);
+	CK(cudaMalloc(&c->sceneBlob, nodeBytes + primBytes + matBytes));
+	c->mats = reinterpret_cast<Mat *>(reinterpret_cast<char *>(c->sceneBlob) + nodeBytes + primBytes);
 	CK(cudaMemcpyAsync(c->sceneBlob, cs.nodes.data(), nodeBytes, cudaMemcpyHostToDevice, c->stream));
 	CK(cudaMemcpyAsync(reinterpret_cast<char *>(c->sceneBlob) + nodeBytes, cs.prims.data(), primBytes, cudaMemcpyHostToDevice, c->stream));
-	CK(cudaMemcpyAsync(c->mats, cs.mats.data(), cs.mats.size() * sizeof(Mat), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(c->mats, cs.mats.data(), matBytes, cudaMemcpyHostToDevice, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
 	c->nodeCount = uint32_t(cs.nodes.size());
 	c->primCount = uint32_t(cs.prims.size());
@@ -472,6 +481,31 @@ static SceneDev sceneDev(const pt_context *c)
 	return s;
 }
 
+// option "env_is": make sure the device holds the importance distribution of the current sky texture (texels read back from the
+// linear device copy the loader keeps)
+static int ensureEnvDistribution(pt_context *c, uint32_t handle)
+{
+	if (c->envHandle == handle && c->envAlias) return PT_OK;
+	const TexDesc &t = c->texHost[handle - 1];
+	const size_t bytes = size_t(t.width) * t.height * (t.isHdr ? 16 : 4);
+	std::vector<unsigned char> texels(bytes);
+	CK(cudaMemcpyAsync(texels.data(), t.texels, bytes, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	EnvDistribution d;
+	buildEnvDistribution(t.width, t.height, t.isHdr != 0, texels.data(), d);
+	if (c->envAlias) { CK(cudaFree(c->envAlias)); c->envAlias = nullptr; }
+	if (c->envDensity) { CK(cudaFree(c->envDensity)); c->envDensity = nullptr; }
+	CK(cudaMalloc(&c->envAlias, d.alias.size() * 4));
+	CK(cudaMalloc(&c->envDensity, d.density.size() * 4));
+	CK(cudaMemcpyAsync(c->envAlias, d.alias.data(), d.alias.size() * 4, cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(c->envDensity, d.density.data(), d.density.size() * 4, cudaMemcpyHostToDevice, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	c->envCols = d.cols;
+	c->envRows = d.rows;
+	c->envHandle = handle;
+	return PT_OK;
+}
+
 static int renderOne(pt_context *c, const CameraDev *camera, uint32_t spp, int ignore_history)
 {
 	PT_TRY
@@ -525,6 +559,17 @@ static int renderOne(pt_context *c, const CameraDev *camera, uint32_t spp, int i
 		}
 		p.beam = c->launch.beam < 0 ? (spp >= 128u ? 1u : 0u) : uint32_t(c->launch.beam != 0);
 		p.alpha = c->alpha;
+		c->launch.envIS = 0;
+		if (c->envIS && p.scene.skybox != 0 && (v == 0 || v == 4 || v == 12))
+		{
+			const int rc = ensureEnvDistribution(c, p.scene.skybox);
+			if (rc != PT_OK) return rc;
+			p.scene.env.alias = static_cast<const uint2 *>(c->envAlias);
+			p.scene.env.density = c->envDensity;
+			p.scene.env.cols = c->envCols;
+			p.scene.env.rows = c->envRows;
+			c->launch.envIS = 1;
+		}
 		if (c->noJitter)
 		{
 			if (!c->centreUV)
@@ -854,6 +899,7 @@ static int setOptionOne(pt_context *c, const char *key, double value)
 	else if (k == "strata_k") c->launch.strataK = value < 2 ? 0 : (value > 10 ? 10 : int(value));
 	else if (k == "smem_stack") c->launch.smemStack = int(value);
 	else if (k == "jitter") c->noJitter = value == 0;
+	else if (k == "env_is") c->envIS = value != 0;
 	else if (k == "first_hit")
 	{
 		c->firstHit = value != 0;
@@ -1063,6 +1109,20 @@ int pt_write_hdr(const char *path, uint32_t width, uint32_t height, const float 
 	if (!path || !rgba) return setError(PT_E_INVALID, "pt_write_hdr: bad arguments");
 	if (!writeHdr(path, width, height, rgba, err)) return setError(PT_E_IO, err);
 	return PT_OK;
+	PT_CATCH(PT_E_LIMIT)
+}
+
+int pt_env_distribution(uint32_t width, uint32_t height, int is_hdr, const void *rgba, uint32_t *cols, uint32_t *rows, uint32_t *alias, float *density)
+{
+	PT_TRY
+	if (!rgba || width == 0 || height == 0) return setError(PT_E_INVALID, "pt_env_distribution: bad arguments");
+	EnvDistribution d;
+	buildEnvDistribution(width, height, is_hdr != 0, rgba, d);
+	if (cols) *cols = d.cols;
+	if (rows) *rows = d.rows;
+	if (alias) memcpy(alias, d.alias.data(), d.alias.size() * 4);
+	if (density) memcpy(density, d.density.data(), d.density.size() * 4);
+	return int(d.density.size());
 	PT_CATCH(PT_E_LIMIT)
 }
 

@@ -173,6 +173,7 @@ void cameraTranslate(pt_camera_desc &c, float x, float y, float z)
 namespace
 {
 constexpr int kBins = 16;
+constexpr size_t kWideNode = size_t(1) << 17, kWideChunk = size_t(1) << 14; // nodes over >= 128 k primitives are analysed in 16 k chunks by all cores
 constexpr float kTraversalCost = 1.0f; // cost of one two-box node fetch + test, in units of...
 constexpr float kHoistFraction = 0.5f; // a primitive whose box has >= this share of the node's box area gets its own leaf at once
 constexpr float kPrimCost = 1.5f;      // ...one primitive intersection (quadric tests are dearer than slab tests)
@@ -202,12 +203,13 @@ struct Builder
 {
 	std::vector<BuildPrim> &bp;
 	std::vector<Node> &nodes;
+	std::vector<uint32_t> subtree; // interior nodes in the subtree of node i, itself included (for the parallel renumbering)
 	std::atomic<uint32_t> nextNode{ 0 };
 	std::atomic<uint32_t> leafCount{ 0 };
 	uint32_t maxLeaf;
 	const pt_object_desc *objects;
 
-	Builder(std::vector<BuildPrim> &b, std::vector<Node> &n, uint32_t ml, const pt_object_desc *o) : bp(b), nodes(n), maxLeaf(ml), objects(o) {}
+	Builder(std::vector<BuildPrim> &b, std::vector<Node> &n, uint32_t ml, const pt_object_desc *o) : bp(b), nodes(n), subtree(n.size()), maxLeaf(ml), objects(o) {}
 
 	int32_t leafRef(size_t begin, size_t count) const
 	{
@@ -219,10 +221,46 @@ struct Builder
 	int32_t build(size_t begin, size_t end, Box &box, uint32_t &depth)
 	{
 		const size_t n = end - begin;
+		// The top of the tree of a large scene: a node over hundreds of thousands of primitives is analysed by ALL cores (chunks of
+		// the range as tasks, results merged in chunk order - boxes and counts are order-independent, the "first largest" rule is
+		// kept by the merge), not by the one thread that happens to own the node: the first levels were a third of the build.
+		const bool wide = n >= kWideNode;
+		const size_t nChunks = wide ? std::min<size_t>(64, (n + kWideChunk - 1) / kWideChunk) : 1;
+		auto chunkRange = [&](size_t c, size_t &b0, size_t &b1) { b0 = begin + n * c / nChunks; b1 = begin + n * (c + 1) / nChunks; };
+		struct Pass1 { Box box, cb, rest, bigBox; float bigArea; size_t big; };
+		struct Pass2 { Box bins[3][kBins]; uint32_t counts[3][kBins]; };
+		std::vector<Pass1> p1;
+		std::vector<Pass2> p2;
 		Box cb;
 		box.reset();
 		cb.reset();
-		for (size_t i = begin; i < end; ++i) { box.grow(bp[i].box); cb.growPoint(bp[i].c); }
+		if (wide)
+		{
+			p1.resize(nChunks);
+			for (size_t c = 0; c < nChunks; ++c)
+			{
+#pragma omp task shared(p1) firstprivate(c)
+				{
+					size_t b0, b1;
+					chunkRange(c, b0, b1);
+					Pass1 &r = p1[c];
+					r.box.reset(); r.cb.reset(); r.rest.reset(); r.bigBox.reset();
+					r.bigArea = -1.0f; r.big = b0;
+					for (size_t i = b0; i < b1; ++i)
+					{
+						r.box.grow(bp[i].box);
+						r.cb.growPoint(bp[i].c);
+						const float a = bp[i].box.area();
+						if (a > r.bigArea) { if (r.bigArea >= 0.0f) r.rest.grow(r.bigBox); r.bigArea = a; r.big = i; r.bigBox = bp[i].box; }
+						else r.rest.grow(bp[i].box);
+					}
+				}
+			}
+#pragma omp taskwait
+			for (const Pass1 &r : p1) { box.grow(r.box); cb.grow(r.cb); }
+		}
+		else
+			for (size_t i = begin; i < end; ++i) { box.grow(bp[i].box); cb.growPoint(bp[i].c); }
 		if (n == 1)
 		{
 			depth = 0;
@@ -234,6 +272,32 @@ struct Builder
 		int bestAxis = -1, bestBin = -1;
 		float bestCost = FLT_MAX;
 		const float parentArea = std::max(box.area(), 1e-30f);
+		if (wide)
+		{
+			p2.resize(nChunks);
+			for (size_t c = 0; c < nChunks; ++c)
+			{
+#pragma omp task shared(p2, cb) firstprivate(c)
+				{
+					size_t b0, b1;
+					chunkRange(c, b0, b1);
+					Pass2 &r = p2[c];
+					for (int axis = 0; axis < 3; ++axis)
+						for (int b = 0; b < kBins; ++b) { r.bins[axis][b].reset(); r.counts[axis][b] = 0; }
+					float k[3];
+					for (int axis = 0; axis < 3; ++axis) { const float ext = cb.mx[axis] - cb.mn[axis]; k[axis] = ext > 0.0f ? float(kBins) / ext : 0.0f; }
+					for (size_t i = b0; i < b1; ++i)
+						for (int axis = 0; axis < 3; ++axis)
+						{
+							int b = int((bp[i].c[axis] - cb.mn[axis]) * k[axis]);
+							b = b < 0 ? 0 : (b > kBins - 1 ? kBins - 1 : b);
+							r.counts[axis][b]++;
+							r.bins[axis][b].grow(bp[i].box);
+						}
+				}
+			}
+#pragma omp taskwait
+		}
 		for (int axis = 0; axis < 3; ++axis)
 		{
 			const float ext = cb.mx[axis] - cb.mn[axis];
@@ -242,6 +306,12 @@ struct Builder
 			uint32_t counts[kBins] = {};
 			for (auto &b : bins) b.reset();
 			const float k = float(kBins) / ext;
+			if (wide)
+			{
+				for (const Pass2 &r : p2)
+					for (int b = 0; b < kBins; ++b) { bins[b].grow(r.bins[axis][b]); counts[b] += r.counts[axis][b]; }
+			}
+			else
 			for (size_t i = begin; i < end; ++i)
 			{
 				int b = int((bp[i].c[axis] - cb.mn[axis]) * k);
@@ -275,10 +345,18 @@ struct Builder
 		{
 			size_t big = begin;
 			float bigArea = -1.0f;
-			for (size_t i = begin; i < end; ++i) { const float a = bp[i].box.area(); if (a > bigArea) { bigArea = a; big = i; } }
 			Box rest;
 			rest.reset();
-			for (size_t i = begin; i < end; ++i) if (i != big) rest.grow(bp[i].box);
+			if (wide)
+			{
+				for (const Pass1 &r : p1) if (r.bigArea > bigArea) { bigArea = r.bigArea; big = r.big; } // strict: the first largest, as below
+				for (const Pass1 &r : p1) { rest.grow(r.rest); if (r.big != big) rest.grow(r.bigBox); }
+			}
+			else
+			{
+				for (size_t i = begin; i < end; ++i) { const float a = bp[i].box.area(); if (a > bigArea) { bigArea = a; big = i; } }
+				for (size_t i = begin; i < end; ++i) if (i != big) rest.grow(bp[i].box);
+			}
 			const float cost = kTraversalCost + kPrimCost * (bigArea + float(n - 1) * rest.area()) / parentArea;
 			// the greedy SAH cost (children costed as leaves) cannot see that damage, so a primitive covering most of the
 			// node is hoisted outright
@@ -354,6 +432,7 @@ struct Builder
 		nd.child[0] = lc;
 		nd.child[1] = rc;
 		nd.pad[0] = nd.pad[1] = 0;
+		subtree[nodeIndex] = 1u + (lc >= 0 ? subtree[size_t(lc)] : 0u) + (rc >= 0 ? subtree[size_t(rc)] : 0u);
 		depth = 1 + std::max(ld, rd);
 		return int32_t(nodeIndex);
 	}
@@ -439,6 +518,7 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 		return false;
 	}
 	out.nodes.resize(b.nextNode.load());
+	if (depth + 2 > uint32_t(kStackSize)) { err = "BVH deeper than the traversal stack"; return false; }
 	// Renumber the nodes: the first kTopOrderNodes in BREADTH-FIRST order (the levels every ray walks sit in a few
 	// consecutive cache lines), the rest depth-first (subtrees contiguous).  Also makes the layout independent of the
 	// order in which the parallel build tasks ran.  (Staging that breadth-first prefix in shared memory for scenes that do
@@ -446,40 +526,48 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 	if (out.nodes.size() > 1)
 	{
 		const size_t n = out.nodes.size();
-		std::vector<int32_t> newIndex(n, -1), order;
-		order.reserve(n);
+		std::vector<int32_t> newIndex(n, -1);
 		std::vector<int32_t> queue;
 		queue.push_back(0);
-		size_t head = 0;
-		while (head < queue.size() && order.size() < kTopOrderNodes)
+		size_t head = 0, numbered = 0;
+		while (head < queue.size() && numbered < kTopOrderNodes)
 		{
 			const int32_t i = queue[head++];
-			newIndex[i] = int32_t(order.size());
-			order.push_back(i);
+			newIndex[i] = int32_t(numbered++);
 			for (int c = 0; c < 2; ++c)
 				if (out.nodes[i].child[c] >= 0) queue.push_back(out.nodes[i].child[c]);
 		}
-		// the frontier (queued but not numbered) and everything below it: depth-first, in queue order
-		std::vector<int32_t> stack;
-		for (size_t q = queue.size(); q-- > head;) stack.push_back(queue[q]);
-		while (!stack.empty())
+		// the frontier (queued but not numbered) and everything below it: depth-first, in queue order.  Every frontier subtree
+		// takes a block of indices whose start follows from the subtree sizes the builder recorded, so the subtrees are numbered
+		// by all cores at once
+		const size_t nFront = queue.size() - head;
+		std::vector<size_t> startOf(nFront + 1);
+		startOf[0] = numbered;
+		for (size_t f = 0; f < nFront; ++f) startOf[f + 1] = startOf[f] + b.subtree[size_t(queue[head + f])];
+		if (startOf[nFront] != n) { err = "internal: BVH renumbering lost nodes"; return false; }
+#pragma omp parallel for schedule(dynamic, 16) if (n > 8192)
+		for (long f = 0; f < long(nFront); ++f)
 		{
-			const int32_t i = stack.back();
-			stack.pop_back();
-			newIndex[i] = int32_t(order.size());
-			order.push_back(i);
-			for (int c = 1; c >= 0; --c)
-				if (out.nodes[i].child[c] >= 0) stack.push_back(out.nodes[i].child[c]);
+			int32_t stack[2 * kStackSize + 8];
+			int sp = 0;
+			stack[sp++] = queue[head + size_t(f)];
+			size_t next = startOf[size_t(f)];
+			while (sp > 0)
+			{
+				const int32_t i = stack[--sp];
+				newIndex[i] = int32_t(next++);
+				for (int c = 1; c >= 0; --c)
+					if (out.nodes[i].child[c] >= 0 && sp < int(sizeof stack / sizeof stack[0])) stack[sp++] = out.nodes[i].child[c];
+			}
 		}
-		if (order.size() != n) { err = "internal: BVH renumbering lost nodes"; return false; }
 		std::vector<Node> renum(n);
 #pragma omp parallel for schedule(static) if (n > 8192)
-		for (long k = 0; k < long(n); ++k)
+		for (long i = 0; i < long(n); ++i)
 		{
-			Node nd = out.nodes[order[k]];
+			Node nd = out.nodes[size_t(i)];
 			for (int c = 0; c < 2; ++c)
 				if (nd.child[c] >= 0) nd.child[c] = newIndex[nd.child[c]];
-			renum[k] = nd;
+			renum[size_t(newIndex[size_t(i)])] = nd;
 		}
 		out.nodes.swap(renum);
 	}
@@ -544,7 +632,6 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 	out.depth = depth;
 	out.leafCount = b.leafCount.load();
 	for (int k = 0; k < 3; ++k) { out.sceneMin[k] = sceneBox.mn[k]; out.sceneMax[k] = sceneBox.mx[k]; }
-	if (depth + 2 > uint32_t(kStackSize)) { err = "BVH deeper than the traversal stack"; return false; }
 
 	out.prims.resize(count);
 	out.mats.resize(count);

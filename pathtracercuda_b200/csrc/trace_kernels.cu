@@ -27,7 +27,9 @@ namespace ptb
 // ---------------------------------------------------------------------------------------------------------------
 // the trace kernel
 // ---------------------------------------------------------------------------------------------------------------
-template <bool SMEM, bool COUNT, int TRAV, bool SHARE, bool SPLIT = false, bool SSTACK = false>
+// ENVIS (option "env_is"): every scattering vertex also samples the sky directly, combined with the BSDF sample by multiple
+// importance sampling (env_sampling.h) - a twin instantiation, so the default kernel's code is untouched by it
+template <bool SMEM, bool COUNT, int TRAV, bool SHARE, bool SPLIT = false, bool SSTACK = false, bool ENVIS = false>
 __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_constant__ RenderParams p)
 {
 	extern __shared__ __align__(128) float4 smemScene[];
@@ -36,12 +38,24 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 	uint32_t smemBase = uint32_t(__cvta_generic_to_shared(smemScene));
 	asm volatile("" : "+r"(smemBase));
 	// SSTACK: this thread's column of the shared-memory traversal stack (trace_device.cuh TravStack<true>), behind the scene copy
+#ifdef PTB_PIN_STACKCOL
+	uint32_t stackColumn = SSTACK ? smemBase + p.stackOffset + threadIdx.x * 4u : 0u;
+	asm volatile("" : "+r"(stackColumn)); // (kept in its register: left alone the compiler recomputes it - S2R, LDC, LEA - at every traversal)
+#else
 	const uint32_t stackColumn = SSTACK ? smemBase + p.stackOffset + threadIdx.x * 4u : 0u;
+#endif
+#ifdef PTB_PIN_WARP
+	uint32_t warpInCta = threadIdx.x >> 5;
+	asm volatile("" : "+r"(warpInCta));
+#define PTB_WARP warpInCta
+#else
+#define PTB_WARP (threadIdx.x >> 5)
+#endif
 	__shared__ uint64_t mbar;
 	SceneView<SMEM> sv;
 	if constexpr (SMEM)
 	{
-		stageSceneToSmem(smemScene, p.scene.sceneBlob, (p.scene.nodeCount + p.scene.primCount) * 64u, &mbar);
+		stageSceneToSmem(smemScene, p.scene.sceneBlob, (p.scene.nodeCount + p.scene.primCount) * 64u + p.scene.primCount * uint32_t(sizeof(Mat)), &mbar);
 		sv.nodes = reinterpret_cast<const float4 *>(uintptr_t(smemBase));
 		sv.prims = sv.nodes + size_t(p.scene.nodeCount) * 4;
 		sv.globalCount = p.scene.globalCount;
@@ -52,6 +66,9 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 		sv.prims = p.scene.sceneBlob + size_t(p.scene.nodeCount) * 4;
 		sv.globalCount = p.scene.globalCount;
 	}
+	// the material table sits behind the primitives, in the shared-memory copy too: the three quads of a material are read once per
+	// path segment, and from L1 / L2 they were a long-scoreboard stall at the head of every shade
+	const float4 *const matTable = sv.prims + size_t(p.scene.primCount) * 4;
 
 	// SHARE: the leaves the camera rays of the warp's pixel can reach (beamLeaves), nearest first
 	__shared__ BeamEntry beamList[SHARE && TRAV >= 1 ? kTraceThreads / 32 : 1][kBeamMax];
@@ -72,6 +89,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 	V3 ro = camO, rd = mk(0.0f, 0.0f, 1.0f), thr = mk(1.0f, 1.0f, 1.0f), L = mk(0.0f, 0.0f, 0.0f);
 	uint32_t bounce = 0, rz = 0, rw = 0, sampleIdx = 0;
 	uint32_t rays = 0, nodeVisits = 0, primTests = 0, shades = 0, misses = 0;
+	float lastPdf = 0.0f;   // ENVIS: pdf with which the BSDF sampled the direction the lane is tracing (weights the sky at a miss)
 	uint32_t wNext = p.spp; // SHARE: next sample of the warp's pixel to hand out (warp-uniform)
 	unsigned long long passStat[6] = { 0, 0, 0, 0, 0, 0 }; // COUNT + SPLIT (lane 0): camera passes, lanes, clocks; scattered passes, lanes, clocks
 	unsigned long long travClk[2] = { 0, 0 };               // COUNT + SPLIT: clocks up to the end of the traversal, camera / scattered passes
@@ -139,7 +157,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 					{
 						uint32_t px, py;
 						pixelToXY(pixel, p.width, p.height, px, py);
-						if (lane == 0) pixelXY[threadIdx.x >> 5] = make_float2(float(px), float(py));
+						if (lane == 0) pixelXY[PTB_WARP] = make_float2(float(px), float(py));
 						__syncwarp();
 					}
 					if constexpr (TRAV >= 1)
@@ -150,7 +168,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 							pixelToXY(pixel, p.width, p.height, px, py);
 							const float m = 1.0f / 64.0f; // footprint widened: the jittered (s, t) are rounded products
 							nBeam = beamLeaves<SMEM>(sv.nodes, p.scene.treeNodeCount, p.scene.nodeCount, p.cam, (float(px) - m) * invW, (float(px) + 1.0f + m) * invW, (float(py) - m) * invH,
-							                         (float(py) + 1.0f + m) * invH, beamList[threadIdx.x >> 5], lane == 0, SMEM ? nullptr : beamBoxes[threadIdx.x >> 5]);
+							                         (float(py) + 1.0f + m) * invH, beamList[PTB_WARP], lane == 0, SMEM ? nullptr : beamBoxes[PTB_WARP]);
 							__syncwarp();
 						}
 					}
@@ -216,7 +234,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 				sampleIdx = p.sampleOffset + sample * p.sampleStride;
 				const uint4 r = philox4x32_10_keyed(pixel, sampleIdx, 0u, 0u, p.philoxKeys);
 				float pxf, pyf;
-				if constexpr (SHARE) { const float2 xy = pixelXY[threadIdx.x >> 5]; pxf = xy.x; pyf = xy.y; }
+				if constexpr (SHARE) { const float2 xy = pixelXY[PTB_WARP]; pxf = xy.x; pyf = xy.y; }
 				else
 				{
 					uint32_t px, py;
@@ -259,10 +277,10 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 			// ---- traverse + intersect (trace.cu:112) ----
 			++rays;
 			const Hit h = TRAV == 0 ? closestHit<SMEM, COUNT, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests)
-			              : TRAV == 1 ? closestHitWW<SMEM, COUNT, false, kHotExact, SSTACK>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? threadIdx.x >> 5 : 0],
-			                                                                                SHARE && bounce == 0 ? nBeam : -1, stackColumn, SMEM ? nullptr : beamBoxes[SHARE ? threadIdx.x >> 5 : 0])
-			                          : closestHitWW<SMEM, COUNT, true, kHotExact, SSTACK>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? threadIdx.x >> 5 : 0],
-			                                                                               SHARE && bounce == 0 ? nBeam : -1, stackColumn, SMEM ? nullptr : beamBoxes[SHARE ? threadIdx.x >> 5 : 0]);
+			              : TRAV == 1 ? closestHitWW<SMEM, COUNT, false, kHotExact, SSTACK>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? PTB_WARP : 0],
+			                                                                                SHARE && bounce == 0 ? nBeam : -1, stackColumn, SMEM ? nullptr : beamBoxes[SHARE ? PTB_WARP : 0])
+			                          : closestHitWW<SMEM, COUNT, true, kHotExact, SSTACK>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? PTB_WARP : 0],
+			                                                                               SHARE && bounce == 0 ? nBeam : -1, stackColumn, SMEM ? nullptr : beamBoxes[SHARE ? PTB_WARP : 0]);
 #ifndef PTB_NO_PARITY_AIDS
 			if ((p.aids & kAidFirstHit) && bounce == 0)
 #else
@@ -289,7 +307,17 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 					// (both inlined: as calls - one copy each, shared with the texture-coordinate code - they cost the hot loop 3 %: two
 					// call / return pairs per miss, and the calling convention fixes registers around them)
 					const float theta = fastAcos(rd.y), phi = fastAtan2Inline(rd.z, rd.x);
-					const V3 sky = texLookup(p.scene.textures, p.scene.skybox, phi * (0.5f / PT_PI), theta * (1.0f / PT_PI));
+					V3 sky = texLookup(p.scene.textures, p.scene.skybox, phi * (0.5f / PT_PI), theta * (1.0f / PT_PI));
+					if constexpr (ENVIS)
+					{
+						// a scattered ray that reaches the sky: the direction could also have come from the sky's own distribution
+						// (balance heuristic; the camera ray's miss has no such rival and keeps weight 1)
+						if (bounce != 0u)
+						{
+							const float pe = envPdf(p.scene.env, phi * (0.5f / PT_PI), theta * (1.0f / PT_PI), rd.y);
+							sky = (lastPdf * rcpApprox(lastPdf + pe)) * sky;
+						}
+					}
 					if constexpr (SHARE) color = color + thr * sky; // the warp's partial sums take every contribution as it comes
 					else L = L + thr * sky;
 				}
@@ -298,8 +326,8 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 			else
 			{
 				// ---- shade / sample (trace.cu:136-151) ----
-				const float4 *mp = reinterpret_cast<const float4 *>(p.scene.mats + h.prim);
-				const float4 m1 = __ldg(mp + 1);
+				const float4 *mp = matTable + h.prim * 3;
+				const float4 m1 = sv.ld(mp + 1);
 				if constexpr (SHARE) color = color + thr * mk(m1.x, m1.y, m1.z); // getEmitted, Material.inl:62-65
 				else L = L + thr * mk(m1.x, m1.y, m1.z);
 				terminate = true;
@@ -310,7 +338,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 				{
 					if (COUNT) ++shades;
 					const Surface s = surfaceAt<SMEM>(sv, h.prim, ro, rd, h.t);
-					const float4 m0 = __ldg(mp), m2 = __ldg(mp + 2);
+					const float4 m0 = sv.ld(mp), m2 = sv.ld(mp + 2);
 					V3 base = mk(m0.x, m0.y, m0.z);
 					const uint32_t tex = __float_as_uint(m2.x), mtype = __float_as_uint(m2.y);
 					if (tex != 0 && tex <= p.scene.texCount)
@@ -328,7 +356,37 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 					}
 					else { rnd0 = uniform01(rz); rnd1 = uniform01(rw); }
 					V3 wi, weight;
-					if (sampleMaterial(mtype, base, m0.w, m1.w, s.n, rd, rnd0, rnd1, wi, weight))
+					bool scattered;
+					if constexpr (ENVIS)
+					{
+						const Frame fr = makeFrame(s.n);
+						const V3 Vv = toTangent(fr, -rd);
+						// one direction from the sky's distribution (its own Philox stream: fourth counter word 1, slot = bounce - the
+						// draws of the path itself are those of a render without "env_is"), the same f and pdf the BSDF sample would
+						// have had for it, and a ray towards it: sky x f x cos / (pdf_sky + pdf_bsdf) if nothing is in the way
+						const uint4 q = philox4x32_10_keyed(pixel, sampleIdx, bounce, 1u, p.philoxKeys);
+						float lu, lv, pe;
+						const V3 wl = sampleEnv(p.scene.env, q.x, q.y, q.z, lu, lv, pe);
+						const V3 sl = toTangent(fr, wl);
+						V3 attL;
+						float pbL;
+						if (sl.z > 0.0f && evalMaterial(mtype, base, m0.w, m1.w, Vv, sl, attL, pbL))
+						{
+							const V3 sky = texLookup(p.scene.textures, p.scene.skybox, lu, lv);
+							const V3 contrib = thr * ((sl.z * rcpApprox(pe + pbL)) * attL) * sky;
+							++rays;
+							uint32_t nv = 0, pt = 0;
+							const Hit hs = closestHitWW<SMEM, false, false, kHotExact, SSTACK>(sv, s.p, wl, 0.001f, nv, pt, beamList[0], -1, stackColumn, nullptr);
+							if (hs.prim < 0)
+							{
+								if constexpr (SHARE) color = color + contrib;
+								else L = L + contrib;
+							}
+						}
+						scattered = sampleMaterial(mtype, base, m0.w, m1.w, fr, Vv, rnd0, rnd1, wi, weight, &lastPdf);
+					}
+					else scattered = sampleMaterial(mtype, base, m0.w, m1.w, s.n, rd, rnd0, rnd1, wi, weight);
+					if (scattered)
 					{
 						thr = thr * weight;
 						ro = s.p;
@@ -499,11 +557,12 @@ constexpr size_t kStaticSmemBound = 36864;
 int launchTrace(const RenderParams &pIn, const LaunchConfig &cfg, cudaStream_t stream, int *usedSmem)
 {
 	RenderParams p = pIn;
-	const size_t sceneBytes = (size_t(p.scene.nodeCount) + p.scene.primCount) * 64;
+	const size_t sceneBytes = (size_t(p.scene.nodeCount) + p.scene.primCount) * 64 + size_t(p.scene.primCount) * sizeof(Mat); // nodes | primitives | materials
 	int variant = cfg.variant;
 	// default: one pixel per warp (camera passes / scattered passes) for renders long enough to amortise the drain at the end of
 	// every pixel (the last paths of a pixel run with the other lanes idle: ~half a path per spp/32 samples), one pixel per lane otherwise
 	if (variant == 0) variant = p.spp >= 64 ? 12 : 4; // measured crossover on generated_scene: 32 spp 15.0 vs 15.2, 64 spp 15.7 vs 15.2, 128 spp 17.8 vs 15.2 Grays/s
+	if (cfg.envIS && variant != 12 && variant != 4) return -1; // "env_is" is built into the two default kernels only
 	const bool stackVariant = variant == 12 || variant == 4; // the two default kernels have shared-memory-stack instantiations
 	const size_t stackBytes = size_t(cfg.stackLevels) * kStackStride;
 	// what goes into shared memory: the scene when it fits (a scene larger than the opt-in limit stays in L2/HBM), the traversal
@@ -513,6 +572,8 @@ int launchTrace(const RenderParams &pIn, const LaunchConfig &cfg, cudaStream_t s
 #define PT_PICK(KERN, ...)                                                                                                        \
 	(smem ? (cfg.countWork ? launchKernel(KERN<true, true __VA_ARGS__>, p, cfg, sb, stream) : launchKernel(KERN<true, false __VA_ARGS__>, p, cfg, sb, stream)) \
 	      : (cfg.countWork ? launchKernel(KERN<false, true __VA_ARGS__>, p, cfg, sb, stream) : launchKernel(KERN<false, false __VA_ARGS__>, p, cfg, sb, stream)))
+	// (the "env_is" twins exist without work counters only)
+#define PT_PICK_NOCOUNT(KERN, ...) (smem ? launchKernel(KERN<true, false __VA_ARGS__>, p, cfg, sb, stream) : launchKernel(KERN<false, false __VA_ARGS__>, p, cfg, sb, stream))
 	for (int attempt = 0; attempt < 3; ++attempt)
 	{
 		if (usedSmem) *usedSmem = smem ? 1 : 0;
@@ -526,9 +587,15 @@ int launchTrace(const RenderParams &pIn, const LaunchConfig &cfg, cudaStream_t s
 		case 8: n = PT_PICK(traceKernel, , 1, true); break;       // one pixel per WARP (lanes = samples), while-while
 		case 9: n = PT_PICK(traceKernel, , 2, true); break;       // one pixel per warp, while-while + leaf parking
 		case 10: n = PT_PICK(traceKernel, , 0, true); break;      // one pixel per warp, if/else traversal
-		case 12: n = sstack ? PT_PICK(traceKernel, , 1, true, true, true) : PT_PICK(traceKernel, , 1, true, true); break; // one pixel per warp, camera passes and scattered passes alternate
+		case 12: // one pixel per warp, camera passes and scattered passes alternate
+			if (cfg.envIS) n = sstack ? PT_PICK_NOCOUNT(traceKernel, , 1, true, true, true, true) : PT_PICK_NOCOUNT(traceKernel, , 1, true, true, false, true);
+			else n = sstack ? PT_PICK(traceKernel, , 1, true, true, true) : PT_PICK(traceKernel, , 1, true, true);
+			break;
 		case 13: n = PT_PICK(traceKernel, , 2, true, true); break; // 12 + leaf parking
-		default: n = sstack ? PT_PICK(traceKernel, , 1, false, false, true) : PT_PICK(traceKernel, , 1, false); break; // 4: one pixel per lane, while-while traversal
+		default: // 4: one pixel per lane, while-while traversal
+			if (cfg.envIS) n = sstack ? PT_PICK_NOCOUNT(traceKernel, , 1, false, false, true, true) : PT_PICK_NOCOUNT(traceKernel, , 1, false, false, false, true);
+			else n = sstack ? PT_PICK(traceKernel, , 1, false, false, true) : PT_PICK(traceKernel, , 1, false);
+			break;
 		}
 		if (n != 0) return n;
 		// the instantiation does not fit with this much shared memory: first without the stack, then without the scene
@@ -537,6 +604,7 @@ int launchTrace(const RenderParams &pIn, const LaunchConfig &cfg, cudaStream_t s
 		else return -1;
 	}
 #undef PT_PICK
+#undef PT_PICK_NOCOUNT
 	return -1;
 }
 

@@ -12,14 +12,23 @@ enum { kCtrWork = 0, kCtrRays = 1, kCtrNodes = 2, kCtrPrims = 3, kCtrShades = 4,
        // their clocks; scattered passes, lanes, clocks; kernel clocks; traversal clocks of camera / scattered passes
        kCtrPassStats = 8, kCtrCount = 24 };
 
+// option "env_is": the sky's importance distribution (env_sampling.h), on the read-only path
+struct EnvDev
+{
+	const uint2 *alias = nullptr; // per cell: (float bits of the acceptance threshold, alias cell)
+	const float *density = nullptr; // per cell: P(cell) cols rows / (2 pi^2); solid-angle pdf = density / sin(theta)
+	uint32_t cols = 0, rows = 0;
+};
+
 struct SceneDev
 {
-	const float4 *sceneBlob = nullptr; // [nodes | prims], 16-byte records, one allocation (bulk-copied to smem)
-	const Mat *mats = nullptr;
+	const float4 *sceneBlob = nullptr; // [nodes | prims | materials], 16-byte records, one allocation (bulk-copied to smem)
+	const Mat *mats = nullptr;         // = the third part of the blob
 	const TexDesc *textures = nullptr;
 	uint32_t nodeCount = 0, primCount = 0, texCount = 0, skybox = 0;
 	uint32_t globalCount = 0; // prims[0..globalCount): tested by every ray before the traversal (pt_types.h)
 	uint32_t treeNodeCount = 0; // nodes[treeNodeCount..nodeCount): boxes of the hoisted primitives, for the pixel-beam walk only
+	EnvDev env;                 // set (alias != nullptr) when the launch samples the sky directly (option "env_is")
 };
 
 struct RenderParams
@@ -72,6 +81,7 @@ struct LaunchConfig
 	int stratify = -1;   // first-bounce stratification (RenderParams::strataPer): 1 on, 0 off, -1 = on from 128 spp (one-pixel-per-warp kernels)
 	int strataK = 0;     // experiments: log2 of the cell count (0 = the rule of pt_render: at least 32 samples per cell, at most 128 cells)
 	int smemStack = -1;  // traversal stack in shared memory (TravStack<true>): 1 on, 0 off, -1 = on when it fits beside the scene
+	int envIS = 0;       // next-event estimation of the sky with multiple importance sampling (RenderParams::scene.env; one-pixel-per-warp kernel)
 	int stackLevels = 0; // BVH depth + 2: levels the shared-memory stack needs (set by pt_render from the compiled scene)
 	size_t maxSmemOptin = 0;
 };

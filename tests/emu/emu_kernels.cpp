@@ -30,6 +30,8 @@ static inline float __uint2float_rn(uint32_t x) { return (float)x; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
 static inline uint32_t __float_as_uint(float f) { uint32_t i; memcpy(&i, &f, 4); return i; }
+static inline float __uint_as_float(uint32_t i) { float f; memcpy(&f, &i, 4); return f; }
+static inline uint32_t __float2uint_rz(float f) { return f > 0.0f ? (uint32_t)f : 0u; }
 static inline void fastSinCos(float x, float *s, float *c) { *s = sinf(x); *c = cosf(x); }
 static inline float fastPow(float a, float b) { return powf(a, b); }
 using std::max;

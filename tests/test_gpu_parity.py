@@ -134,6 +134,42 @@ def test_render_matches_oracle_path_for_path(scene, W, H, spp):
     assert imgio.rmse(a / spp, b / spp)[0] < 0.02
 
 
+@pytest.mark.parametrize("W,H,spp", [(96, 54, 32), (80, 45, 256)])
+def test_env_importance_sampling_matches_oracle_path_for_path(W, H, spp):
+    """option "env_is" (sky importance sampling + multiple importance sampling; not in the reference): the CUDA path against the
+    oracle's restatement of the same estimator, same Philox counters -> same paths, same light samples, same shadow rays; both
+    kernels that carry it (one pixel per lane below 64 spp, one pixel per warp above).  And against the plain render: same mean."""
+    earth, sky = _assets()
+    objs, cam = _scene("generated_scene", W, H)
+    O = orc.Oracle(objs)
+    O.add_texture(earth)
+    O.set_skybox(O.add_texture(sky))
+    plain, _ = O.render(cam, W, H, spp)
+    O.set_env_is(1)
+    a, ra = O.render(cam, W, H, spp)
+    with pt.Pathtracer(W, H) as P:
+        cam2 = P.loadSceneFile(f"{pt.ASSETS}/scenes/generated_scene.json", cwd=pt.ASSETS)
+        P.setOption("env_is", 1)
+        P.render(cam2, spp, True)
+        b = P.getHDRMean() * spp
+        st = P.stats()
+        P.render(cam2, spp, True)
+        b2 = P.getHDRMean() * spp
+        P.setOption("env_is", 0)
+        P.render(cam2, spp, True)
+        c = P.getHDRMean() * spp
+        st0 = P.stats()
+    assert np.array_equal(bits(b), bits(b2))                      # deterministic
+    assert abs(int(st.rays) - int(ra)) <= 1e-3 * ra and st.rays > st0.rays and st.samples == W * H * spp
+    rel = np.abs(a - b)[..., :3] / (np.abs(a[..., :3]) + 1e-3 * spp)
+    assert (rel.max(-1) > 1e-3 * max(1.0, spp / 64)).mean() < 0.05
+    assert abs(a[..., :3].mean() / b[..., :3].mean() - 1) < 2e-3
+    assert imgio.rmse(a / spp, b / spp)[0] < 0.02
+    # the same picture as without the option, less noise in it (against the oracle's plain render: an independent estimate)
+    assert abs(b[..., :3].mean() / c[..., :3].mean() - 1) < 0.02
+    assert not np.array_equal(bits(b), bits(c))
+
+
 @pytest.mark.parametrize("scene", ["cornell_box", "generated_scene"])
 def test_converged_image_within_reference_noise_floor(scene):
     """north_star gate: RMSE(ours, reference) <= 1.1 x RMSE(reference seed A, reference seed B) at 4096 spp on linear HDR,
