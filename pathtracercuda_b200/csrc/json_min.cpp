@@ -341,9 +341,10 @@ bool scanJsonNumber(const char *text, size_t n, size_t &i, double &value, bool &
 	return true;
 }
 
-bool parseJson(const std::string &text, JsonValue &out, std::string &err)
+bool parseJson(const std::string &text, JsonValue &out, std::string &err) { return parseJson(text.data(), text.size(), out, err); }
+bool parseJson(const char *text, size_t n, JsonValue &out, std::string &err)
 {
-	Parser p{ text.data(), text.size() };
+	Parser p{ text, n };
 	// nlohmann skips a UTF-8 byte-order mark
 	if (p.n >= 3 && (unsigned char)p.s[0] == 0xEF && (unsigned char)p.s[1] == 0xBB && (unsigned char)p.s[2] == 0xBF) p.i = 3;
 	if (!p.value(out)) { err = p.err; return false; }

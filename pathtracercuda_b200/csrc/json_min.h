@@ -61,6 +61,7 @@ inline const JsonValue *JsonValue::find(const char *key) const
 
 // Parses `text`; on failure returns false and describes the error (with byte offset) in `err`.
 bool parseJson(const std::string &text, JsonValue &out, std::string &err);
+bool parseJson(const char *text, size_t n, JsonValue &out, std::string &err); // (the text need not be null-terminated: a mapped file)
 // Parses the ONE value that fills text[begin, end) (blanks around it allowed), sequentially.  For the streaming scene reader.
 bool parseJsonSpan(const char *text, size_t begin, size_t end, JsonValue &out);
 // Scans one JSON number at text[i...] (i < n, text[i] is '-' or a digit): value as a double (as parseJson produces it), whether

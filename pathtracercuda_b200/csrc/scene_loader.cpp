@@ -16,10 +16,24 @@
 #include <fstream>
 #include <sstream>
 
+#include <chrono>
+#include <cstdlib>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 namespace ptb
 {
 namespace
 {
+// PTB_TIMING=1: phase timings of the loader on stderr
+struct LoaderLap
+{
+	bool on = getenv("PTB_TIMING") != nullptr;
+	double last = now();
+	static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+	void operator()(const char *what) { if (on) { const double t = now(); fprintf(stderr, "  loadScene    %-14s %7.1f ms\n", what, (t - last) * 1e3); last = t; } }
+};
 float radiansf(float degree) { return degree * (1.0f / 180.0f) * 3.14159265358979323846f; }
 
 bool getString(const JsonValue &o, const char *key, std::string &out)
@@ -274,10 +288,8 @@ size_t structuralScan(const char *s, size_t begin, size_t end, ScanState &st, lo
 }
 
 // Locates "objects": [ ... ] in the top-level object and splits it.  arrBegin / arrEnd = positions of its brackets.
-bool splitObjectsArray(const std::string &text, size_t &arrBegin, size_t &arrEnd, std::vector<size_t> &starts)
+bool splitObjectsArray(const char *s, const size_t n, size_t &arrBegin, size_t &arrEnd, std::vector<size_t> &starts)
 {
-	const char *s = text.data();
-	const size_t n = text.size();
 	// (1) the key, by a scan of the top-level object's members
 	size_t i = 0;
 	if (n >= 3 && (unsigned char)s[0] == 0xEF && (unsigned char)s[1] == 0xBB && (unsigned char)s[2] == 0xBF) i = 3;
@@ -315,7 +327,8 @@ bool splitObjectsArray(const std::string &text, size_t &arrBegin, size_t &arrEnd
 		}
 		if (!c.eat(',')) return false;
 	}
-	// (2) pass 1: per chunk, both hypotheses
+	// (2) whether a chunk starts inside a string: the parity of the unescaped quotes in front of it (memchr speed; a chunk never
+	// starts behind a backslash, so a run of backslashes is never cut)
 	const size_t from = arrBegin + 1;
 	int threads = 1;
 #ifdef _OPENMP
@@ -330,52 +343,97 @@ bool splitObjectsArray(const std::string &text, size_t &arrBegin, size_t &arrEnd
 		bound[k] = std::min(b, n);
 	}
 	bound[nChunks] = n;
-	std::vector<ScanState> res(nChunks * 2);
+	std::vector<size_t> quotes(nChunks);
 #pragma omp parallel for schedule(dynamic, 1)
 	for (long k = 0; k < long(nChunks); ++k)
-		for (int h = 0; h < 2; ++h)
+	{
+		size_t count = 0;
+		const char *p = s + bound[k], *e = s + bound[k + 1];
+		while (p < e && (p = static_cast<const char *>(memchr(p, '"', size_t(e - p)))) != nullptr)
 		{
-			ScanState st{ h == 1, 0, 0 };
-			structuralScan(s, bound[k], bound[k + 1], st, LONG_MIN, false, 0, [](size_t) {});
-			res[size_t(k) * 2 + h] = st;
+			size_t slashes = 0;
+			for (const char *q = p; q > s + bound[k] && q[-1] == '\\'; --q) ++slashes;
+			if ((slashes & 1u) == 0u) ++count;
+			++p;
 		}
-	// serial prefix: true start state of every chunk, and the chunk in which the array closes (depth -1)
-	std::vector<ScanState> startOf(nChunks);
-	bool inStr = false;
+		quotes[size_t(k)] = count;
+	}
+	// (3) ONE structural scan per chunk, from depth 0: the commas at the lowest depth the chunk reaches are its candidates for the
+	// array's top-level commas (they are the ones exactly when that lowest depth is the array's own level, which the prefix over
+	// the chunks' depth changes tells afterwards)
+	struct ChunkScan { long depth, minDepth; std::vector<size_t> commas; };
+	std::vector<ChunkScan> scan(nChunks);
+	{
+		std::vector<char> startsInString(nChunks);
+		size_t q = 0;
+		for (size_t k = 0; k < nChunks; ++k) { startsInString[k] = char(q & 1u); q += quotes[k]; }
+#pragma omp parallel for schedule(dynamic, 1)
+		for (long k = 0; k < long(nChunks); ++k)
+		{
+			ChunkScan &cs = scan[size_t(k)];
+			bool inString = startsInString[size_t(k)] != 0;
+			long depth = 0, minDepth = 0;
+			static const struct Structural { bool is[256]; Structural() : is() { for (const char *z = "\"[]{},\\"; *z; ++z) is[(unsigned char)*z] = true; } } structural;
+			size_t j = bound[k];
+			const size_t end = bound[k + 1];
+			while (j < end)
+			{
+				if (inString)
+				{
+					while (j < end && s[j] != '"' && s[j] != '\\') ++j;
+					if (j >= end) break;
+					if (s[j] == '\\') { j += 2; continue; }
+					inString = false;
+					++j;
+					continue;
+				}
+				while (j < end && !structural.is[(unsigned char)s[j]]) ++j;
+				if (j >= end) break;
+				const char ch = s[j];
+				if (ch == '"') inString = true;
+				else if (ch == '[' || ch == '{') ++depth;
+				else if (ch == ']' || ch == '}') { if (--depth < minDepth) { minDepth = depth; cs.commas.clear(); } }
+				else if (ch == ',' && depth == minDepth) cs.commas.push_back(j);
+				++j;
+			}
+			cs.depth = depth;
+			cs.minDepth = minDepth;
+		}
+	}
+	// serial prefix: absolute depth at the start of every chunk, and the chunk in which the array closes (depth -1)
+	std::vector<long> depthAt(nChunks);
 	long depth = 0;
 	size_t lastChunk = nChunks;
 	for (size_t k = 0; k < nChunks; ++k)
 	{
-		startOf[k] = ScanState{ inStr, depth, 0 };
-		const ScanState &r = res[k * 2 + (inStr ? 1 : 0)];
-		if (depth + r.minDepth < 0) { lastChunk = k; break; }
-		depth += r.depth;
-		inStr = r.inString;
+		depthAt[k] = depth;
+		if (depth + scan[k].minDepth < 0) { lastChunk = k; break; }
+		depth += scan[k].depth;
 	}
 	if (lastChunk == nChunks) return false; // the array never closes
-	// (3) pass 2: the top-level commas
-	std::vector<std::vector<size_t>> commas(lastChunk + 1);
+	// the closing chunk holds text behind the array as well: scanned once more, with its known start state, up to the bracket
+	std::vector<size_t> lastCommas;
 	size_t closeAt = 0;
-#pragma omp parallel for schedule(dynamic, 1)
-	for (long k = 0; k <= long(lastChunk); ++k)
 	{
-		ScanState st = startOf[size_t(k)];
-		st.minDepth = st.depth;
-		std::vector<size_t> &mine = commas[size_t(k)];
-		const size_t stop = structuralScan(s, bound[k], bound[k + 1], st, 0, size_t(k) == lastChunk, 0, [&mine](size_t pos) { mine.push_back(pos); });
-		if (size_t(k) == lastChunk) closeAt = stop;
+		size_t q = 0;
+		for (size_t k = 0; k < lastChunk; ++k) q += quotes[k];
+		ScanState st{ (q & 1u) != 0u, depthAt[lastChunk], depthAt[lastChunk] };
+		closeAt = structuralScan(s, bound[lastChunk], bound[lastChunk + 1], st, 0, true, 0, [&lastCommas](size_t pos) { lastCommas.push_back(pos); });
 	}
 	if (closeAt >= n || s[closeAt] != ']') return false;
 	arrEnd = closeAt;
 	starts.clear();
 	starts.push_back(from);
-	for (const std::vector<size_t> &v : commas)
-		for (size_t pos : v) starts.push_back(pos + 1);
+	for (size_t k = 0; k < lastChunk; ++k)
+		if (depthAt[k] + scan[k].minDepth == 0) // the chunk reaches the array's own level
+			for (size_t pos : scan[k].commas) starts.push_back(pos + 1);
+	for (size_t pos : lastCommas) starts.push_back(pos + 1);
 	return true;
 }
 } // namespace
 
-bool parseSceneText(const std::string &text, float aspect, ParsedScene &out, std::string &err)
+bool parseSceneText(const std::string &text, float aspect, ParsedScene &out, std::string &err) { return parseSceneText(text.data(), text.size(), aspect, out, err); }
+bool parseSceneText(const char *textData, const size_t textSize, float aspect, ParsedScene &out, std::string &err)
 {
 	out = ParsedScene();
 	auto textureHandle = [&](const std::string &p) -> uint32_t
@@ -408,19 +466,21 @@ bool parseSceneText(const std::string &text, float aspect, ParsedScene &out, std
 	bool streamed = false;
 	size_t arrBegin = 0, arrEnd = 0;
 	std::vector<size_t> starts;
-	if (text.size() >= (size_t(4) << 20) && splitObjectsArray(text, arrBegin, arrEnd, starts))
+	LoaderLap lap;
+	if (textSize >= (size_t(4) << 20) && splitObjectsArray(textData, textSize, arrBegin, arrEnd, starts))
 	{
+		lap("split array");
 		// the rest of the document, with the array cut out
 		std::string rest;
-		rest.reserve(arrBegin + (text.size() - arrEnd) + 2);
-		rest.append(text, 0, arrBegin);
+		rest.reserve(arrBegin + (textSize - arrEnd) + 2);
+		rest.append(textData, arrBegin);
 		rest += "[]";
-		rest.append(text, arrEnd + 1, std::string::npos);
+		rest.append(textData + arrEnd + 1, textSize - arrEnd - 1);
 		std::string restErr;
 		const JsonValue *ro = nullptr;
 		if (parseJson(rest, root, restErr) && (ro = root.find("objects")) != nullptr && ro->kind == JsonValue::Array && ro->arr().empty())
 		{
-			const char *s = text.data();
+			const char *s = textData;
 			// "[ ]": one blank element
 			size_t count = starts.size();
 			if (count == 1)
@@ -452,6 +512,7 @@ bool parseSceneText(const std::string &text, float aspect, ParsedScene &out, std
 					if (i < bad) { bad = i; firstErr = e2; }
 				}
 			}
+			lap("objects");
 			if (!syntaxError)
 			{
 				streamed = true;
@@ -468,7 +529,7 @@ bool parseSceneText(const std::string &text, float aspect, ParsedScene &out, std
 	}
 	if (!streamed)
 	{
-		if (!parseJson(text, root, err)) return false;
+		if (!parseJson(textData, textSize, root, err)) return false;
 		const JsonValue *objs = root.find("objects");
 		if (objs && objs->kind == JsonValue::Array)
 		{
@@ -528,18 +589,44 @@ bool parseSceneFile(const char *path, float aspect, ParsedScene &out, std::strin
 		if (errCode) *errCode = PT_E_IO;
 		return false;
 	}
-	// one read into one buffer (a million-object scene file is hundreds of megabytes)
-	std::string text;
-	f.seekg(0, std::ios::end);
-	const std::streamoff size = f.tellg();
-	f.seekg(0, std::ios::beg);
-	if (size > 0)
+	f.close();
+	// the file is MAPPED, not read: a million-object scene is hundreds of megabytes, and copying it out of the page cache into a
+	// zero-filled buffer was a third of the load time; the loader's threads fault the pages in as they scan them
+	LoaderLap lapRead;
+	const int fd = open(path, O_RDONLY);
+	struct stat st;
+	if (fd < 0 || fstat(fd, &st) != 0)
 	{
-		text.resize(size_t(size));
-		f.read(&text[0], size);
-		text.resize(size_t(f.gcount()));
+		if (fd >= 0) close(fd);
+		err = std::string("Failed to open input file: ") + path;
+		if (errCode) *errCode = PT_E_IO;
+		return false;
 	}
-	if (!parseSceneText(text, aspect, out, err))
+	const size_t size = size_t(st.st_size);
+	void *map = size ? mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0) : nullptr;
+	std::string small;
+	const char *text = "";
+	if (size && map == MAP_FAILED)
+	{
+		// (a file system that cannot map: read it)
+		map = nullptr;
+		small.resize(size);
+		size_t got = 0;
+		while (got < size) { const ssize_t r = pread(fd, &small[got], size - got, off_t(got)); if (r <= 0) break; got += size_t(r); }
+		small.resize(got);
+		text = small.data();
+	}
+	else if (size)
+	{
+		madvise(map, size, MADV_SEQUENTIAL | MADV_WILLNEED);
+		text = static_cast<const char *>(map);
+	}
+	close(fd);
+	lapRead("map file");
+	const size_t textSize = map ? size : small.size();
+	const bool ok = parseSceneText(text, textSize, aspect, out, err);
+	if (map) munmap(map, size);
+	if (!ok)
 	{
 		if (errCode) *errCode = PT_E_PARSE;
 		return false;

@@ -19,4 +19,5 @@ struct ParsedScene
 
 bool parseSceneFile(const char *path, float aspect, ParsedScene &out, std::string &err, int *errCode);
 bool parseSceneText(const std::string &text, float aspect, ParsedScene &out, std::string &err);
+bool parseSceneText(const char *text, size_t n, float aspect, ParsedScene &out, std::string &err); // (need not be null-terminated)
 } // namespace ptb
