@@ -197,7 +197,9 @@ const float *pt_get_hdr_sum(pt_context *ctx);
  *  "jitter"          0: every sample goes through the pixel centre, u = (x + 0.5) / W (parity aid; default 1 = trace.cu:190-191)
  *  "first_hit"       1: pt_render also records, per pixel, the scene index and t of the closest hit of the camera ray AS FOUND BY
  *                    THE RENDER KERNEL ITSELF (pt_get_first_hit); with "jitter" = 0 this is the primary-pass gate on the
- *                    production traversal (beams, MUFU reciprocals and all)
+ *                    production traversal (beams, MUFU reciprocals and all).  Both aids are compiled into a twin instantiation
+ *                    of the default kernels (variant 0 / 4 / 12) - same template, same arguments - which renders the same bits
+ *                    as the instantiation without them (checked in tests/test_gpu_baseline_sizes.py)
  *  "env_is"          1: every scattering vertex also draws one direction from the sky's importance distribution
  *                    (pt_env_distribution) and the sky light reaching it is estimated by multiple importance sampling (balance
  *                    heuristic) of that draw and the BSDF's own.  The same integral as the reference's estimator (paths of at

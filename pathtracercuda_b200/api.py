@@ -61,6 +61,8 @@ def load_library():
         "pt_version": (cp, []),
     }
     for name, (res, args) in sig.items():
+        if os.environ.get("PT_B200_LIB") and not hasattr(L, name):
+            continue  # (an experiment build of an older revision, tools/exp.py: it may lack the newest entry points)
         fn = getattr(L, name)  # AttributeError here = the library does not export what include/pt_b200.h declares
         fn.restype = res
         fn.argtypes = args

@@ -588,6 +588,9 @@ static int renderOne(pt_context *c, const CameraDev *camera, uint32_t spp, int i
 		p.firstHitIndex = c->firstHit ? c->firstHitIndex : nullptr;
 		p.firstHitT = c->firstHit ? c->firstHitT : nullptr;
 		if (c->firstHit) p.aids |= kAidFirstHit;
+		if (p.aids && !(v == 0 || v == 4 || v == 12))
+			return setError(PT_E_INVALID, "pt_render: the parity aids (jitter = 0, first_hit = 1) are built into the default kernels only (variant 0, 4 or 12)");
+		if (p.aids && c->launch.envIS) return setError(PT_E_INVALID, "pt_render: the parity aids and env_is cannot be combined");
 		c->launch.stackLevels = int(c->bvhDepth) + 2;
 		CK(cudaEventRecord(c->evStart, c->stream)); // (all allocations are behind us: the events bracket the device work alone)
 		// pixel partition: the pixels of the other ranks hold zeros, so that the sum over ranks is the image

@@ -29,7 +29,10 @@ namespace ptb
 // ---------------------------------------------------------------------------------------------------------------
 // ENVIS (option "env_is"): every scattering vertex also samples the sky directly, combined with the BSDF sample by multiple
 // importance sampling (env_sampling.h) - a twin instantiation, so the default kernel's code is untouched by it
-template <bool SMEM, bool COUNT, int TRAV, bool SHARE, bool SPLIT = false, bool SSTACK = false, bool ENVIS = false>
+// AIDS: the parity aids (options "jitter" = 0, "first_hit" = 1) are compiled into a twin instantiation as well: in the kernel
+// that is benchmarked their two never-taken branches cost 1.5 % (measured: 6.5 of 435 ms; profiles/r02c_microvariants_run22.txt).
+// The twin is the same template with the same arguments; tests/test_gpu_baseline_sizes.py checks that both render the same bits.
+template <bool SMEM, bool COUNT, int TRAV, bool SHARE, bool SPLIT = false, bool SSTACK = false, bool ENVIS = false, bool AIDS = false>
 __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_constant__ RenderParams p)
 {
 	extern __shared__ __align__(128) float4 smemScene[];
@@ -243,12 +246,11 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 				}
 				float u = (pxf + uniform01(r.x)) * invW; // trace.cu:190
 				float v = (pyf + uniform01(r.y)) * invH;
-#ifndef PTB_NO_PARITY_AIDS
 				// option "jitter" = 0 (parity aid): every sample through the pixel centre, u = (x + 0.5) / W with the IEEE division of the
 				// reference's primary pass - read from two small tables the host worked out (a division routine here, even out of
 				// line, cost the hot loop 2 %: its call constrains the register allocation of everything around it)
-				if (p.aids & kAidPixelCentre) { u = __ldg(p.centreU + __float2uint_rz(pxf)); v = __ldg(p.centreV + __float2uint_rz(pyf)); }
-#endif
+				if constexpr (AIDS)
+					if (p.aids & kAidPixelCentre) { u = __ldg(p.centreU + __float2uint_rz(pxf)); v = __ldg(p.centreV + __float2uint_rz(pyf)); }
 				rz = r.z; rw = r.w;
 				if constexpr (SHARE)
 				{
@@ -281,15 +283,14 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 			                                                                                SHARE && bounce == 0 ? nBeam : -1, stackColumn, SMEM ? nullptr : beamBoxes[SHARE ? PTB_WARP : 0])
 			                          : closestHitWW<SMEM, COUNT, true, kHotExact, SSTACK>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? PTB_WARP : 0],
 			                                                                               SHARE && bounce == 0 ? nBeam : -1, stackColumn, SMEM ? nullptr : beamBoxes[SHARE ? PTB_WARP : 0]);
-#ifndef PTB_NO_PARITY_AIDS
-			if ((p.aids & kAidFirstHit) && bounce == 0)
-#else
-			if (false)
-#endif
+			if constexpr (AIDS)
 			{
 				// parity aid: what THIS kernel's traversal found for the camera ray (scene-order index, t), per pixel
-				p.firstHitIndex[pixel] = h.prim < 0 ? -1 : int32_t(primSceneIndex(sv.ld(sv.prims + h.prim * 4 + 3)));
-				p.firstHitT[pixel] = h.prim < 0 ? 0.0f : h.t;
+				if ((p.aids & kAidFirstHit) && bounce == 0)
+				{
+					p.firstHitIndex[pixel] = h.prim < 0 ? -1 : int32_t(primSceneIndex(sv.ld(sv.prims + h.prim * 4 + 3)));
+					p.firstHitT[pixel] = h.prim < 0 ? 0.0f : h.t;
+				}
 			}
 
 			if constexpr (COUNT && SPLIT)
@@ -370,20 +371,27 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 						const V3 sl = toTangent(fr, wl);
 						V3 attL;
 						float pbL;
-						if (sl.z > 0.0f && evalMaterial(mtype, base, m0.w, m1.w, Vv, sl, attL, pbL))
+						V3 contrib = mk(0.0f, 0.0f, 0.0f);
+						const bool lit = sl.z > 0.0f && evalMaterial(mtype, base, m0.w, m1.w, Vv, sl, attL, pbL);
+						if (lit)
 						{
 							const V3 sky = texLookup(p.scene.textures, p.scene.skybox, lu, lv);
-							const V3 contrib = thr * ((sl.z * rcpApprox(pe + pbL)) * attL) * sky;
+							contrib = thr * ((sl.z * rcpApprox(pe + pbL)) * attL) * sky;
+						}
+						// (the BSDF sample first, the shadow ray behind it: frame, view vector and material are dead by then and only
+						// the light sample's direction and value live across the walk)
+						scattered = sampleMaterial(mtype, base, m0.w, m1.w, fr, Vv, rnd0, rnd1, wi, weight, &lastPdf);
+						if (lit)
+						{
 							++rays;
 							uint32_t nv = 0, pt = 0;
-							const Hit hs = closestHitWW<SMEM, false, false, kHotExact, SSTACK>(sv, s.p, wl, 0.001f, nv, pt, beamList[0], -1, stackColumn, nullptr);
+							const Hit hs = closestHitWW<SMEM, false, false, kHotExact, SSTACK, true>(sv, s.p, wl, 0.001f, nv, pt, beamList[0], -1, stackColumn, nullptr);
 							if (hs.prim < 0)
 							{
 								if constexpr (SHARE) color = color + contrib;
 								else L = L + contrib;
 							}
 						}
-						scattered = sampleMaterial(mtype, base, m0.w, m1.w, fr, Vv, rnd0, rnd1, wi, weight, &lastPdf);
 					}
 					else scattered = sampleMaterial(mtype, base, m0.w, m1.w, s.n, rd, rnd0, rnd1, wi, weight);
 					if (scattered)
@@ -562,7 +570,8 @@ int launchTrace(const RenderParams &pIn, const LaunchConfig &cfg, cudaStream_t s
 	// default: one pixel per warp (camera passes / scattered passes) for renders long enough to amortise the drain at the end of
 	// every pixel (the last paths of a pixel run with the other lanes idle: ~half a path per spp/32 samples), one pixel per lane otherwise
 	if (variant == 0) variant = p.spp >= 64 ? 12 : 4; // measured crossover on generated_scene: 32 spp 15.0 vs 15.2, 64 spp 15.7 vs 15.2, 128 spp 17.8 vs 15.2 Grays/s
-	if (cfg.envIS && variant != 12 && variant != 4) return -1; // "env_is" is built into the two default kernels only
+	if ((cfg.envIS || p.aids) && variant != 12 && variant != 4) return -1; // "env_is" and the parity aids are built into the two default kernels only
+	if (cfg.envIS && p.aids) return -1;                                    // (and not into one twin together)
 	const bool stackVariant = variant == 12 || variant == 4; // the two default kernels have shared-memory-stack instantiations
 	const size_t stackBytes = size_t(cfg.stackLevels) * kStackStride;
 	// what goes into shared memory: the scene when it fits (a scene larger than the opt-in limit stays in L2/HBM), the traversal
@@ -588,12 +597,14 @@ int launchTrace(const RenderParams &pIn, const LaunchConfig &cfg, cudaStream_t s
 		case 9: n = PT_PICK(traceKernel, , 2, true); break;       // one pixel per warp, while-while + leaf parking
 		case 10: n = PT_PICK(traceKernel, , 0, true); break;      // one pixel per warp, if/else traversal
 		case 12: // one pixel per warp, camera passes and scattered passes alternate
-			if (cfg.envIS) n = sstack ? PT_PICK_NOCOUNT(traceKernel, , 1, true, true, true, true) : PT_PICK_NOCOUNT(traceKernel, , 1, true, true, false, true);
+			if (p.aids) n = sstack ? PT_PICK_NOCOUNT(traceKernel, , 1, true, true, true, false, true) : PT_PICK_NOCOUNT(traceKernel, , 1, true, true, false, false, true);
+			else if (cfg.envIS) n = sstack ? PT_PICK_NOCOUNT(traceKernel, , 1, true, true, true, true) : PT_PICK_NOCOUNT(traceKernel, , 1, true, true, false, true);
 			else n = sstack ? PT_PICK(traceKernel, , 1, true, true, true) : PT_PICK(traceKernel, , 1, true, true);
 			break;
 		case 13: n = PT_PICK(traceKernel, , 2, true, true); break; // 12 + leaf parking
 		default: // 4: one pixel per lane, while-while traversal
-			if (cfg.envIS) n = sstack ? PT_PICK_NOCOUNT(traceKernel, , 1, false, false, true, true) : PT_PICK_NOCOUNT(traceKernel, , 1, false, false, false, true);
+			if (p.aids) n = sstack ? PT_PICK_NOCOUNT(traceKernel, , 1, false, false, true, false, true) : PT_PICK_NOCOUNT(traceKernel, , 1, false, false, false, false, true);
+			else if (cfg.envIS) n = sstack ? PT_PICK_NOCOUNT(traceKernel, , 1, false, false, true, true) : PT_PICK_NOCOUNT(traceKernel, , 1, false, false, false, true);
 			else n = sstack ? PT_PICK(traceKernel, , 1, false, false, true) : PT_PICK(traceKernel, , 1, false);
 			break;
 		}

@@ -63,6 +63,16 @@ def test_production_kernel_first_hit_vs_reference_hitbvh(name, tmp_path):
         idx, t = P.firstHit()
         st = P.stats()
         exact_idx, exact_t = P.primaryPass(cam)
+        # The parity aids live in a twin instantiation of the kernel template (same source, same template arguments otherwise;
+        # csrc/trace_kernels.cu AIDS): with the ray generation left alone ("jitter" = 1) the twin (first_hit = 1) and the
+        # instantiation that is benchmarked (first_hit = 0) must render the very same bits - the twin's traversal IS the
+        # production traversal
+        P.setOption("jitter", 1)
+        P.render(cam, 128, True)
+        twin = P.getHDRSum().copy()
+        P.setOption("first_hit", 0)
+        P.render(cam, 128, True)
+        assert np.array_equal(twin.view(np.uint32), P.getHDRSum().view(np.uint32)), "the aids twin and the production kernel disagree"
     assert st.samples == W * H * 128
     mism = np.nonzero(idx != ref_idx)[0]
     # How many pixels may differ.  Up to 100 k objects: a handful (measured 1 ... 31).  The 1 M-object scene is seen from 300 ... 1100
