@@ -560,7 +560,7 @@ static int launchKernel(K kern, const RenderParams &p, const LaunchConfig &cfg, 
 
 // static shared memory of the trace kernels (beam lists, per-warp pixel coordinates, barrier; + the beam boxes of
 // the global-memory instantiations) - an upper bound; launchKernel has the last word (occupancy query)
-constexpr size_t kStaticSmemBound = 36864;
+constexpr size_t kStaticSmemBound = 8192; // (the instantiations that stage the scene carry 4.5 KB: the beam boxes belong to the global-memory ones)
 
 int launchTrace(const RenderParams &pIn, const LaunchConfig &cfg, cudaStream_t stream, int *usedSmem)
 {

@@ -376,12 +376,12 @@ def test_first_bounce_stratification_is_unbiased_and_deterministic():
 
 
 def test_scene_sizes_around_the_shared_memory_opt_in_window():
-    """scenes of 150 ... 3200 objects: node + primitive records of 14 ... 300 KB.  Between 28 and 48 KB the scene fits the default
-    dynamic limit only without the kernels' ~20 KB of static shared memory (the opt-in has to be requested whenever dynamic
-    shared memory is used); around 130-200 KB the scene fits but scene + shared-memory stack may not; beyond ~200 KB it stays in
-    global memory.  Every size must render, finite, with the same rays per sample either way."""
+    """scenes of 150 ... 3200 objects: node + primitive + material records (176 B per object) of 26 ... 560 KB.  Between 28 and 48 KB
+    the scene fits the default dynamic limit only without the kernels' static shared memory (the opt-in has to be requested
+    whenever dynamic shared memory is used); around 130-220 KB the scene fits but scene + shared-memory stack may not; beyond
+    ~220 KB it stays in global memory.  Every size must render, finite, with the same rays per sample either way."""
     W, H = 96, 54
-    for n in (150, 300, 400, 700, 1500, 3200):
+    for n in (150, 300, 400, 700, 1100, 1500, 3200):
         objs, cam = scenegen.synthetic_scene(n, W, H)
         res = []
         for smem in (1, 0):
@@ -394,7 +394,7 @@ def test_scene_sizes_around_the_shared_memory_opt_in_window():
                 res.append((P.getHDRMean(), P.stats(), st8))
         (a, sa, sa8), (b, sb, sb8) = res
         assert np.isfinite(a).all() and sa.rays == sb.rays and sa8.rays == sb8.rays, n
-        assert sb.scene_in_smem == 0 and sa.scene_in_smem == (1 if n <= 1500 else 0), (n, sa.scene_bytes)
+        assert sb.scene_in_smem == 0 and sa.scene_in_smem == (1 if n <= 1100 else 0), (n, sa.scene_bytes)
         assert np.allclose(a, b, rtol=1e-4, atol=1e-5), n
 
 
