@@ -201,15 +201,15 @@ struct BuildPrim
 
 struct Builder
 {
-	std::vector<BuildPrim> &bp;
-	std::vector<Node> &nodes;
+	RecordVector<BuildPrim> &bp;
+	RecordVector<Node> &nodes;
 	std::vector<uint32_t> subtree; // interior nodes in the subtree of node i, itself included (for the parallel renumbering)
 	std::atomic<uint32_t> nextNode{ 0 };
 	std::atomic<uint32_t> leafCount{ 0 };
 	uint32_t maxLeaf;
 	const pt_object_desc *objects;
 
-	Builder(std::vector<BuildPrim> &b, std::vector<Node> &n, uint32_t ml, const pt_object_desc *o) : bp(b), nodes(n), subtree(n.size()), maxLeaf(ml), objects(o) {}
+	Builder(RecordVector<BuildPrim> &b, RecordVector<Node> &n, uint32_t ml, const pt_object_desc *o) : bp(b), nodes(n), subtree(n.size()), maxLeaf(ml), objects(o) {}
 
 	int32_t leafRef(size_t begin, size_t count) const
 	{
@@ -450,8 +450,8 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 	if (count > kLeafStartMask) { err = "too many objects"; return false; }
 	maxLeaf = std::max(1u, std::min(maxLeaf, kMaxLeafPrims));
 
-	std::vector<ObjectXform> xf(count);
-	std::vector<BuildPrim> bp(count);
+	RecordVector<ObjectXform> xf(count); // (both filled by the parallel loop below)
+	RecordVector<BuildPrim> bp(count);
 #pragma omp parallel for schedule(static) if (count > 4096)
 	for (long i = 0; i < long(count); ++i)
 	{
@@ -488,7 +488,7 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 	out.globalCount = uint32_t(nGlobal);
 
 	lap("hoist");
-	out.nodes.assign(std::max<size_t>(count, 2) - 1 + 1, Node());
+	out.nodes.resize(std::max<size_t>(count, 2) - 1 + 1); // (not cleared: the builder writes every node it hands out)
 	lap("alloc nodes");
 	Builder b(bp, out.nodes, maxLeaf, objects);
 	Box rootBox;
@@ -509,6 +509,7 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 		// (converted below to centre +FLT_MAX / half extent -1)
 		nd.child[0] = root;
 		nd.child[1] = kEmptyChild;
+		nd.pad[0] = nd.pad[1] = 0;
 		b.nextNode = 1;
 		depth = 1;
 	}
@@ -519,6 +520,35 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 	}
 	out.nodes.resize(b.nextNode.load());
 	if (depth + 2 > uint32_t(kStackSize)) { err = "BVH deeper than the traversal stack"; return false; }
+	// min/max -> centre / half extent, padded outwards: the traversal computes t_c = c*inv - o*inv in fp32, so the box
+	// must absorb a few ulp of |c|, of its own size and of the scene scale (ray origins) to stay conservative.  Applied to every
+	// node on its way into its final place (the renumbering copy below; the records appended behind the tree).
+	float boxScale = 0.0f;
+	for (int k = 0; k < 3; ++k) boxScale = std::max(boxScale, std::max(fabsf(sceneBox.mn[k]), fabsf(sceneBox.mx[k])));
+	auto toCentreHalf = [boxScale](Node &nd)
+	{
+		float mm[12]; // as the builder left them: child c = min[3] max[3] at 6 * c
+		memcpy(mm, nd.f, sizeof mm);
+		for (int c = 0; c < 2; ++c)
+		{
+			const float *f = mm + 6 * c;
+			for (int k = 0; k < 3; ++k)
+			{
+				if (nd.child[c] == kEmptyChild)
+				{
+					nd.f[nodeF(c, 0, k)] = FLT_MAX;
+					nd.f[nodeF(c, 1, k)] = -1.0f;
+					continue;
+				}
+				const double mn = f[k], mx = f[3 + k];
+				const float ctr = float(0.5 * (mn + mx));
+				double h = std::max(mx - double(ctr), double(ctr) - mn); // covers the rounding of the centre
+				h += 4.0e-7 * (fabs(double(ctr)) + h + double(boxScale)) + 1e-30;
+				nd.f[nodeF(c, 0, k)] = ctr;                              // interleaved layout of pt_types.h
+				nd.f[nodeF(c, 1, k)] = nextafterf(float(h), FLT_MAX);
+			}
+		}
+	};
 	// Renumber the nodes: the first kTopOrderNodes in BREADTH-FIRST order (the levels every ray walks sit in a few
 	// consecutive cache lines), the rest depth-first (subtrees contiguous).  Also makes the layout independent of the
 	// order in which the parallel build tasks ran.  (Staging that breadth-first prefix in shared memory for scenes that do
@@ -560,17 +590,19 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 					if (out.nodes[i].child[c] >= 0 && sp < int(sizeof stack / sizeof stack[0])) stack[sp++] = out.nodes[i].child[c];
 			}
 		}
-		std::vector<Node> renum(n);
+		RecordVector<Node> renum(n);
 #pragma omp parallel for schedule(static) if (n > 8192)
 		for (long i = 0; i < long(n); ++i)
 		{
 			Node nd = out.nodes[size_t(i)];
 			for (int c = 0; c < 2; ++c)
 				if (nd.child[c] >= 0) nd.child[c] = newIndex[nd.child[c]];
+			toCentreHalf(nd);
 			renum[size_t(newIndex[size_t(i)])] = nd;
 		}
 		out.nodes.swap(renum);
 	}
+	else toCentreHalf(out.nodes[0]);
 	lap("renumber");
 	// the hoisted primitives' boxes, two per record, behind the tree: the pixel-beam walk decides with them which hoisted
 	// primitives the camera rays of a pixel have to test at all
@@ -593,42 +625,9 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 			}
 		}
 		nd.pad[0] = nd.pad[1] = 0;
+		toCentreHalf(nd);
 		out.nodes.push_back(nd);
 	}
-	// min/max -> centre / half extent, padded outwards: the traversal computes t_c = c*inv - o*inv in fp32, so the box
-	// must absorb a few ulp of |c|, of its own size and of the scene scale (ray origins) to stay conservative
-	{
-		float scale = 0.0f;
-		for (int k = 0; k < 3; ++k) scale = std::max(scale, std::max(fabsf(sceneBox.mn[k]), fabsf(sceneBox.mx[k])));
-		const long nn = long(out.nodes.size());
-#pragma omp parallel for schedule(static) if (nn > 8192)
-		for (long q = 0; q < nn; ++q)
-		{
-			Node &nd = out.nodes[size_t(q)];
-			float mm[12]; // as the builder left them: child c = min[3] max[3] at 6 * c
-			memcpy(mm, nd.f, sizeof mm);
-			for (int c = 0; c < 2; ++c)
-			{
-				const float *f = mm + 6 * c;
-				for (int k = 0; k < 3; ++k)
-				{
-					if (nd.child[c] == kEmptyChild)
-					{
-						nd.f[nodeF(c, 0, k)] = FLT_MAX;
-						nd.f[nodeF(c, 1, k)] = -1.0f;
-						continue;
-					}
-					const double mn = f[k], mx = f[3 + k];
-					const float ctr = float(0.5 * (mn + mx));
-					double h = std::max(mx - double(ctr), double(ctr) - mn); // covers the rounding of the centre
-					h += 4.0e-7 * (fabs(double(ctr)) + h + double(scale)) + 1e-30;
-					nd.f[nodeF(c, 0, k)] = ctr;                              // interleaved layout of pt_types.h
-					nd.f[nodeF(c, 1, k)] = nextafterf(float(h), FLT_MAX);
-				}
-			}
-		}
-	}
-	lap("centre/half");
 	out.depth = depth;
 	out.leafCount = b.leafCount.load();
 	for (int k = 0; k < 3; ++k) { out.sceneMin[k] = sceneBox.mn[k]; out.sceneMax[k] = sceneBox.mx[k]; }

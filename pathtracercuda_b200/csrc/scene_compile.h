@@ -2,19 +2,34 @@
 #pragma once
 #include "../../include/pt_b200.h"
 #include "pt_types.h"
+#include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace ptb
 {
 
+// std::vector without the zero fill: resize() of these record arrays (tens to hundreds of megabytes for a million objects) default-
+// initialises - every element is written by the compiler before it is read - instead of clearing memory on one thread first
+template <typename T>
+struct DefaultInitAllocator : std::allocator<T>
+{
+	template <typename U> struct rebind { using other = DefaultInitAllocator<U>; };
+	DefaultInitAllocator() = default;
+	template <typename U> DefaultInitAllocator(const DefaultInitAllocator<U> &) {}
+	template <typename U> void construct(U *p) { ::new (static_cast<void *>(p)) U; }
+	template <typename U, typename... A> void construct(U *p, A &&...a) { ::new (static_cast<void *>(p)) U(std::forward<A>(a)...); }
+};
+template <typename T> using RecordVector = std::vector<T, DefaultInitAllocator<T>>;
+
 struct CompiledScene
 {
-	std::vector<Node> nodes;  // nodes[0..treeNodeCount): the tree; then one record per PAIR of hoisted primitives (their boxes + leaf
+	RecordVector<Node> nodes;  // nodes[0..treeNodeCount): the tree; then one record per PAIR of hoisted primitives (their boxes + leaf
 	                          // references), which no tree node points to: only the pixel-beam walk reads them (trace_device.cuh)
 	uint32_t treeNodeCount = 0;
-	std::vector<Prim> prims; // BVH order
-	std::vector<Mat> mats;   // BVH order (parallel to prims)
+	RecordVector<Prim> prims; // BVH order
+	RecordVector<Mat> mats;   // BVH order (parallel to prims)
 	uint32_t depth = 0;      // interior-node depth (max traversal stack = depth)
 	uint32_t leafCount = 0;
 	uint32_t globalCount = 0; // prims[0..globalCount) are tested by every ray before the traversal and are not in the BVH
