@@ -41,19 +41,9 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 	uint32_t smemBase = uint32_t(__cvta_generic_to_shared(smemScene));
 	asm volatile("" : "+r"(smemBase));
 	// SSTACK: this thread's column of the shared-memory traversal stack (trace_device.cuh TravStack<true>), behind the scene copy
-#ifdef PTB_PIN_STACKCOL
-	uint32_t stackColumn = SSTACK ? smemBase + p.stackOffset + threadIdx.x * 4u : 0u;
-	asm volatile("" : "+r"(stackColumn)); // (kept in its register: left alone the compiler recomputes it - S2R, LDC, LEA - at every traversal)
-#else
+	// (pinning this address, or the warp's index, in a register - as is done for smemBase - was measured: no gain / +1.3 ms; the
+	// compiler recomputes both where they are used)
 	const uint32_t stackColumn = SSTACK ? smemBase + p.stackOffset + threadIdx.x * 4u : 0u;
-#endif
-#ifdef PTB_PIN_WARP
-	uint32_t warpInCta = threadIdx.x >> 5;
-	asm volatile("" : "+r"(warpInCta));
-#define PTB_WARP warpInCta
-#else
-#define PTB_WARP (threadIdx.x >> 5)
-#endif
 	__shared__ uint64_t mbar;
 	SceneView<SMEM> sv;
 	if constexpr (SMEM)
@@ -160,7 +150,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 					{
 						uint32_t px, py;
 						pixelToXY(pixel, p.width, p.height, px, py);
-						if (lane == 0) pixelXY[PTB_WARP] = make_float2(float(px), float(py));
+						if (lane == 0) pixelXY[(threadIdx.x >> 5)] = make_float2(float(px), float(py));
 						__syncwarp();
 					}
 					if constexpr (TRAV >= 1)
@@ -171,7 +161,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 							pixelToXY(pixel, p.width, p.height, px, py);
 							const float m = 1.0f / 64.0f; // footprint widened: the jittered (s, t) are rounded products
 							nBeam = beamLeaves<SMEM>(sv.nodes, p.scene.treeNodeCount, p.scene.nodeCount, p.cam, (float(px) - m) * invW, (float(px) + 1.0f + m) * invW, (float(py) - m) * invH,
-							                         (float(py) + 1.0f + m) * invH, beamList[PTB_WARP], lane == 0, SMEM ? nullptr : beamBoxes[PTB_WARP]);
+							                         (float(py) + 1.0f + m) * invH, beamList[(threadIdx.x >> 5)], lane == 0, SMEM ? nullptr : beamBoxes[(threadIdx.x >> 5)]);
 							__syncwarp();
 						}
 					}
@@ -237,7 +227,7 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 				sampleIdx = p.sampleOffset + sample * p.sampleStride;
 				const uint4 r = philox4x32_10_keyed(pixel, sampleIdx, 0u, 0u, p.philoxKeys);
 				float pxf, pyf;
-				if constexpr (SHARE) { const float2 xy = pixelXY[PTB_WARP]; pxf = xy.x; pyf = xy.y; }
+				if constexpr (SHARE) { const float2 xy = pixelXY[(threadIdx.x >> 5)]; pxf = xy.x; pyf = xy.y; }
 				else
 				{
 					uint32_t px, py;
@@ -279,10 +269,10 @@ __global__ void __launch_bounds__(kTraceThreads, 1) traceKernel(const __grid_con
 			// ---- traverse + intersect (trace.cu:112) ----
 			++rays;
 			const Hit h = TRAV == 0 ? closestHit<SMEM, COUNT, kHotExact>(sv, ro, rd, 0.001f, nodeVisits, primTests)
-			              : TRAV == 1 ? closestHitWW<SMEM, COUNT, false, kHotExact, SSTACK>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? PTB_WARP : 0],
-			                                                                                SHARE && bounce == 0 ? nBeam : -1, stackColumn, SMEM ? nullptr : beamBoxes[SHARE ? PTB_WARP : 0])
-			                          : closestHitWW<SMEM, COUNT, true, kHotExact, SSTACK>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? PTB_WARP : 0],
-			                                                                               SHARE && bounce == 0 ? nBeam : -1, stackColumn, SMEM ? nullptr : beamBoxes[SHARE ? PTB_WARP : 0]);
+			              : TRAV == 1 ? closestHitWW<SMEM, COUNT, false, kHotExact, SSTACK>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? (threadIdx.x >> 5) : 0],
+			                                                                                SHARE && bounce == 0 ? nBeam : -1, stackColumn, SMEM ? nullptr : beamBoxes[SHARE ? (threadIdx.x >> 5) : 0])
+			                          : closestHitWW<SMEM, COUNT, true, kHotExact, SSTACK>(sv, ro, rd, 0.001f, nodeVisits, primTests, beamList[SHARE ? (threadIdx.x >> 5) : 0],
+			                                                                               SHARE && bounce == 0 ? nBeam : -1, stackColumn, SMEM ? nullptr : beamBoxes[SHARE ? (threadIdx.x >> 5) : 0]);
 			if constexpr (AIDS)
 			{
 				// parity aid: what THIS kernel's traversal found for the camera ray (scene-order index, t), per pixel

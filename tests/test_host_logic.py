@@ -134,6 +134,13 @@ def test_scene_loader_quirks(tmp_path):
             pt.parse_scene_file(str(p), 4, 4)
     with pytest.raises(pt.PtError, match="Failed to open input file"):
         pt.parse_scene_file(str(tmp_path / "missing.json"), 4, 4)
+    # the file is mapped, not read: an empty file, blanks only, a directory
+    for content in ("", "   \n"):
+        p.write_text(content)
+        with pytest.raises(pt.PtError, match="JSON parse error at byte \\d+: unexpected end of input"):
+            pt.parse_scene_file(str(p), 4, 4)
+    with pytest.raises(pt.PtError, match="JSON parse error"):
+        pt.parse_scene_file(str(tmp_path), 4, 4)
     p.write_text('{"objects": [{"position": ["x", 0, 0]}]}')
     with pytest.raises(pt.PtError, match="type must be number"):
         pt.parse_scene_file(str(p), 4, 4)
