@@ -185,6 +185,9 @@ const float *pt_get_hdr_sum(pt_context *ctx);
  *  "smem_scene"      0: never stage the scene in shared memory; 1: auto (default)
  *  "max_bounces"     path segments, default 5 (kernels/trace.cu:109)
  *  "max_leaf"        primitives per BVH leaf at most (default 4, the reference's Pathtracer.cpp:121; set before the scene)
+ *  "bvh_builder"     0: binned SAH, as good a tree as the reference's (BVH.cpp:66-228); 1: LBVH - Morton order of the centroids +
+ *                    Karras' radix tree, one primitive per leaf - built by all cores in a tenth of the time, traversal ~2 % slower
+ *                    (measured on 10 k ... 1 M objects); 2 (default): LBVH from 2^19 objects, SAH below (set before the scene)
  *  "max_global"      how many scene-spanning primitives are hoisted out of the BVH (default 8; set before the scene)
  *  "variant"         trace kernel variant, 0 = default (see csrc/trace_kernels.h LaunchConfig)
  *  "beam"            pixel beams for camera rays (one-pixel-per-warp kernels): 1 on, 0 off, -1 auto (default: on from 128 spp)

@@ -3,7 +3,7 @@
 // same output files.  The windowed branch (-window / -enable_controls, main.cpp:298-437) needs GLFW/OpenGL and is
 // out of scope on a headless B200 server: the flags are parsed and reported, then refused.
 // Extra options use a double dash so they cannot collide with the reference's: --device N, --seed S, --slice N,
-// --true-mean, --stats, --env-is (sky importance sampling, pt_set_option "env_is"), and for several GPUs of one box (the reference is fixed to device 0, Pathtracer.cpp:40):
+// --true-mean, --stats, --env-is (sky importance sampling, pt_set_option "env_is"), --bvh sah|lbvh|auto, and for several GPUs of one box (the reference is fixed to device 0, Pathtracer.cpp:40):
 // --gpus N (devices 0..N-1) or --devices MASK, --partition pixels|samples, --exchange p2p|nccl (pt_create_multi).
 #include "../../include/pt_b200.h"
 #include <algorithm>
@@ -29,6 +29,7 @@ struct Params // reference Params.h:4-14
 	bool trueMean = false;
 	bool stats = false;
 	bool envIS = false;
+	int bvhBuilder = 2; // pt_set_option "bvh_builder": 0 sah, 1 lbvh, 2 auto (the library's default)
 	unsigned int deviceMask = 0; // != 0: multi-GPU context over these CUDA ordinals
 	int partition = 0;           // 0 pixels, 1 samples
 	int exchange = -1;           // -1 auto, 0 nccl, 1 p2p
@@ -74,6 +75,7 @@ static bool processArgs(int argc, char *argv[], Params &params)
 		else if (strcmp(a, "--exchange") == 0 && i + 1 < argc) { params.exchange = strcmp(argv[i + 1], "nccl") == 0 ? 0 : (strcmp(argv[i + 1], "p2p") == 0 ? 1 : -1); i += 2; }
 		else if (strcmp(a, "--true-mean") == 0) { params.trueMean = true; ++i; }
 		else if (strcmp(a, "--env-is") == 0) { params.envIS = true; ++i; }
+		else if (strcmp(a, "--bvh") == 0 && i + 1 < argc) { const char *v = argv[i + 1]; params.bvhBuilder = strcmp(v, "lbvh") == 0 ? 1 : (strcmp(v, "auto") == 0 ? 2 : 0); i += 2; }
 		else if (strcmp(a, "--stats") == 0) { params.stats = true; ++i; }
 		else
 		{
@@ -156,6 +158,7 @@ int main(int argc, char *argv[])
 	// of CALLS (quirk Q1); one launch here counts as ceil(spp/8) calls.  --true-mean writes the real mean instead.
 	pt_set_option(ctx, "frames_per_spp", 8.0);
 	if (params.envIS) pt_set_option(ctx, "env_is", 1.0);
+	pt_set_option(ctx, "bvh_builder", (double)params.bvhBuilder);
 
 	pt_camera_desc camera;
 	const int lr = pt_load_scene_file(ctx, params.m_inputFilepath, &camera);

@@ -56,6 +56,7 @@ struct pt_context
 	float4 *sceneBlob = nullptr;
 	Mat *mats = nullptr;
 	uint32_t nodeCount = 0, treeNodeCount = 0, primCount = 0, bvhDepth = 0, globalCount = 0, maxGlobal = ptb::kMaxGlobalPrims;
+	int bvhBuilder = ptb::kBuilderAuto; // option "bvh_builder" (scene_compile.h): SAH, from 2^19 objects the LBVH
 	// textures
 	std::vector<void *> texMem;
 	TexDesc texHost[kMaxTextures];
@@ -321,7 +322,7 @@ int pt_set_scene(pt_context *c, size_t count, const pt_object_desc *objects)
 	if (!objects) return setError(PT_E_INVALID, "pt_set_scene: null objects");
 	CompiledScene cs;
 	std::string err;
-	if (!compileScene(count, objects, c->maxLeaf, cs, err, c->maxGlobal)) return setError(PT_E_LIMIT, "pt_set_scene: " + err);
+	if (!compileScene(count, objects, c->maxLeaf, cs, err, c->maxGlobal, nullptr, c->bvhBuilder)) return setError(PT_E_LIMIT, "pt_set_scene: " + err);
 	// the BVH is built ONCE on the host; a multi-GPU context replicates the compiled scene on every device
 	int r = uploadScene(c, cs);
 	for (size_t i = 0; r == PT_OK && i < c->peers.size(); ++i) r = uploadScene(c->peers[i], cs);
@@ -354,7 +355,7 @@ int pt_set_scene_xform(pt_context *c, size_t count, const pt_object_xform_desc *
 	}
 	CompiledScene cs;
 	std::string err;
-	if (!compileScene(count, descs.data(), c->maxLeaf, cs, err, c->maxGlobal, xf.data())) return setError(PT_E_LIMIT, "pt_set_scene_xform: " + err);
+	if (!compileScene(count, descs.data(), c->maxLeaf, cs, err, c->maxGlobal, xf.data(), c->bvhBuilder)) return setError(PT_E_LIMIT, "pt_set_scene_xform: " + err);
 	int r = uploadScene(c, cs);
 	for (size_t i = 0; r == PT_OK && i < c->peers.size(); ++i) r = uploadScene(c->peers[i], cs);
 	return r;
@@ -895,6 +896,7 @@ static int setOptionOne(pt_context *c, const char *key, double value)
 	else if (k == "max_leaf") c->maxLeaf = value < 1 ? 1u : uint32_t(value);
 	else if (k == "variant") c->launch.variant = int(value);
 	else if (k == "max_global") c->maxGlobal = uint32_t(value < 0 ? 0 : value);
+	else if (k == "bvh_builder") c->bvhBuilder = value == 1 ? kBuilderLbvh : (value == 0 ? kBuilderSah : kBuilderAuto);
 	else if (k == "regen_low") c->launch.regenLow = int(value);
 	else if (k == "beam") c->launch.beam = int(value);
 	else if (k == "alpha") c->alpha = float(value);

@@ -52,8 +52,12 @@ void computeObjectXform(const pt_object_desc &d, ObjectXform &out);
 // maxLeaf in [1, kMaxLeafPrims].  Returns false and sets err on failure (depth over kStackSize).
 // `given` != nullptr: the objects' transforms and world boxes as the caller has them (pt_set_scene_xform: only w2l, bmin, bmax
 // are read) instead of deriving them from position / rotation / scale.
+// `builder`: kBuilderSah (binned SAH, the default), kBuilderLbvh (Morton order + Karras' radix tree: a several times faster build, a
+// somewhat slower traversal), kBuilderAuto (LBVH from kLbvhAutoCount objects).
+enum { kBuilderSah = 0, kBuilderLbvh = 1, kBuilderAuto = 2 };
+constexpr size_t kLbvhAutoCount = size_t(1) << 19;
 bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf, CompiledScene &out, std::string &err, uint32_t maxGlobal = kMaxGlobalPrims,
-                  const ObjectXform *given = nullptr);
+                  const ObjectXform *given = nullptr, int builder = kBuilderSah);
 
 // Camera ctor + update() equivalent (reference Camera.inl:4-23,54-62)
 void computeCamera(const pt_camera_desc &c, CameraDev &out);

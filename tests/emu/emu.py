@@ -20,12 +20,14 @@ def build():
 
 
 class Emu:
-    def __init__(self, objects, max_leaf=4):
+    def __init__(self, objects, max_leaf=4, builder=0):
         build()
         L = C.CDLL(SO)
         self.L = L
         L.emu_scene_create.restype = C.c_void_p
         L.emu_scene_create.argtypes = [C.c_size_t, C.c_void_p, C.c_uint32]
+        L.emu_scene_create2.restype = C.c_void_p
+        L.emu_scene_create2.argtypes = [C.c_size_t, C.c_void_p, C.c_uint32, C.c_int]
         L.emu_scene_destroy.argtypes = [C.c_void_p]
         L.emu_add_texture.restype = C.c_uint32
         L.emu_add_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p]
@@ -38,7 +40,7 @@ class Emu:
         L.emu_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p]
         self.n = len(objects)
         self._arr = object_array(objects)
-        self.s = L.emu_scene_create(self.n, C.byref(self._arr), max_leaf)
+        self.s = L.emu_scene_create2(self.n, C.byref(self._arr), max_leaf, builder)  # builder: scene_compile.h kBuilderSah / kBuilderLbvh
         assert self.s, "compileScene failed"
         self._keep = []
 

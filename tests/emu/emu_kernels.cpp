@@ -68,11 +68,13 @@ static uint64_t g_beamStats[4] = { 0, 0, 0, 0 }; // pixels, list entries, overfl
 
 extern "C"
 {
-void *emu_scene_create(size_t n, const pt_object_desc *objs, uint32_t maxLeaf)
+void *emu_scene_create2(size_t n, const pt_object_desc *objs, uint32_t maxLeaf, int builder);
+void *emu_scene_create(size_t n, const pt_object_desc *objs, uint32_t maxLeaf) { return emu_scene_create2(n, objs, maxLeaf, kBuilderSah); }
+void *emu_scene_create2(size_t n, const pt_object_desc *objs, uint32_t maxLeaf, int builder)
 {
 	EmuScene *s = new EmuScene();
 	std::string err;
-	if (!compileScene(n, objs, maxLeaf, s->cs, err)) { delete s; return nullptr; }
+	if (!compileScene(n, objs, maxLeaf, s->cs, err, kMaxGlobalPrims, nullptr, builder)) { delete s; return nullptr; }
 	s->blob.resize((s->cs.nodes.size() + s->cs.prims.size()) * 4);
 	memcpy(s->blob.data(), s->cs.nodes.data(), s->cs.nodes.size() * 64);
 	memcpy(s->blob.data() + s->cs.nodes.size() * 4, s->cs.prims.data(), s->cs.prims.size() * 64);

@@ -375,6 +375,38 @@ def test_first_bounce_stratification_is_unbiased_and_deterministic():
     assert np.array_equal(bits(run(-1, spp=64)[0]), bits(run(0, spp=64)[0]))
 
 
+def test_lbvh_builder_finds_the_same_hits(tmp_path):
+    """option "bvh_builder" = 1 (Morton order + Karras' radix tree instead of the binned SAH): another tree over the same primitives,
+    so the closest hit of every ray is the same - the IEEE primary pass agrees bit for bit, the production kernel's first hits agree,
+    a path-traced image agrees up to the paths whose hit is decided by float rounding in the box tests"""
+    W, H = 480, 270
+    os.symlink(pt.ASSETS + "/skybox.hdr", str(tmp_path / "skybox.hdr"))
+    scenegen.write_synthetic_scene(str(tmp_path / "scene.json"), 30000)
+    res = {}
+    for builder in (0, 1):
+        with pt.Pathtracer(W, H) as P:
+            P.setOption("bvh_builder", builder)
+            cam = P.loadSceneFile(str(tmp_path / "scene.json"), cwd=str(tmp_path))
+            idx, t = P.primaryPass(cam)
+            P.setOption("jitter", 0)
+            P.setOption("first_hit", 1)
+            P.render(cam, 128, True)
+            fi, ft = P.firstHit()
+            P.setOption("jitter", 1)
+            P.setOption("first_hit", 0)
+            P.render(cam, 128, True)
+            res[builder] = (idx, t, fi, ft, P.getHDRMean(), P.stats())
+    a, b = res[0], res[1]
+    assert b[5].bvh_nodes >= a[5].bvh_nodes and b[5].bvh_depth < 46      # one primitive per leaf: at least as many nodes
+    assert np.array_equal(a[0], b[0]) and np.array_equal(bits(a[1]), bits(b[1]))
+    assert (a[2] != b[2]).mean() < 1e-5 and np.allclose(a[3], b[3], rtol=1e-5, atol=1e-6)
+    assert abs(int(a[5].rays) - int(b[5].rays)) <= 1e-3 * a[5].rays
+    rel = np.abs(a[4] - b[4])[..., :3] / (np.abs(a[4][..., :3]) + 1e-3)
+    share, means = float((rel.max(-1) > 1e-3).mean()), float(a[4][..., :3].mean() / b[4][..., :3].mean())
+    print(f"lbvh vs sah: nodes {b[5].bvh_nodes} / {a[5].bvh_nodes}, depth {b[5].bvh_depth} / {a[5].bvh_depth}, first hits differing {(a[2] != b[2]).sum()}, pixels beyond 1e-3: {share:.4f}, mean ratio {means:.6f}")
+    assert share < 0.02 and abs(means - 1) < 1e-3, (share, means)
+
+
 def test_scene_sizes_around_the_shared_memory_opt_in_window():
     """scenes of 150 ... 3200 objects: node + primitive + material records (176 B per object) of 26 ... 560 KB.  Between 28 and 48 KB
     the scene fits the default dynamic limit only without the kernels' static shared memory (the opt-in has to be requested

@@ -193,8 +193,8 @@ def _area(b):
     return 2 * (e[0] * e[1] + e[0] * e[2] + e[1] * e[2])
 
 
-def _validate_bvh(objs, max_leaf=4):
-    E = Emu(objs, max_leaf)
+def _validate_bvh(objs, max_leaf=4, builder=0):
+    E = Emu(objs, max_leaf, builder)
     nodes, prims = E.arrays()
     O = orc.Oracle(objs)
     boxes = np.array([O.object_info(i)[1] for i in range(len(objs))])
@@ -273,6 +273,18 @@ def test_bvh_structure():
     _validate_bvh([pt.make_object("SPHERE")])                        # a single object: root with one empty child
     _validate_bvh([pt.make_object("CUBE")] * 9, max_leaf=2)          # coincident centroids: median fallback
     _validate_bvh([pt.make_object("QUAD", position=(i, 0, 0)) for i in range(5)], max_leaf=8)
+    # the LBVH builder (Morton order + Karras' radix tree, option "bvh_builder" = 1): the same invariants, one primitive per leaf,
+    # also with coincident centroids (equal Morton keys: ties broken by position) and the smallest trees
+    for name in ("cornell_box", "generated_scene"):
+        objs, _ = golden_objects(load_golden(name))
+        _validate_bvh(objs, max_leaf=1, builder=1)
+    objs, _ = scenegen.synthetic_scene(3000, 64, 36)
+    n2, d2, l2 = _validate_bvh(objs, max_leaf=1, builder=1)
+    assert d2 < 46 and l2 >= leaves
+    _validate_bvh([pt.make_object("SPHERE")], builder=1)
+    _validate_bvh([pt.make_object("SPHERE"), pt.make_object("CUBE", position=(3, 0, 0))], max_leaf=1, builder=1)
+    _validate_bvh([pt.make_object("CUBE")] * 9, max_leaf=1, builder=1)
+    _validate_bvh([pt.make_object("QUAD", position=(i, 0, 0)) for i in range(5)], max_leaf=1, builder=1)
 
 
 def test_cli_arguments():

@@ -4,6 +4,7 @@
 #include "scene_loader.h"
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <omp.h>
 using namespace ptb;
 static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -19,7 +20,7 @@ int main(int argc, char **argv)
 		if (!parseSceneFile(argv[1], 16.0f / 9.0f, ps, err, &code)) { printf("parse failed: %s\n", err.c_str()); return 1; }
 		const double t1 = now();
 		CompiledScene cs;
-		if (!compileScene(ps.objects.size(), ps.objects.data(), 4, cs, err)) { printf("compile failed: %s\n", err.c_str()); return 1; }
+		if (!compileScene(ps.objects.size(), ps.objects.data(), 4, cs, err, kMaxGlobalPrims, nullptr, argc > 2 ? atoi(argv[2]) : 0)) { printf("compile failed: %s\n", err.c_str()); return 1; }
 		const double t2 = now();
 		printf("threads %d objects %zu: parse %.3f s, compile %.3f s (nodes %zu, depth %u)\n", omp_get_max_threads(), ps.objects.size(), t1 - t0, t2 - t1, cs.nodes.size(), cs.depth);
 	}
