@@ -301,6 +301,9 @@ def test_cli_arguments():
     assert r.returncode == 0 and "Invalid input for -w!" in r.stdout
     r = subprocess.run([CLI, "-bogus", "x.json"], capture_output=True, text=True)
     assert r.returncode == 0 and "Can't parse argument: -bogus" in r.stdout
+    # the double-dash extras are understood (what happens next needs a GPU: here the context cannot be created)
+    r = subprocess.run([CLI, "--env-is", "--bvh", "lbvh", "--seed", "7", "--stats", "-w", "8", "-h", "8", "x.json"], capture_output=True, text=True)
+    assert "Can't parse argument" not in r.stdout and "Width: 8" in r.stdout
 
 
 def test_synthetic_generator_deterministic(tmp_path):
