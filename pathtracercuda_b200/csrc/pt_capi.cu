@@ -174,10 +174,13 @@ int pt_create(uint32_t width, uint32_t height, int device, pt_context **out)
 	const size_t px = size_t(width) * height;
 #define CKC(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { char buf[512]; snprintf(buf, sizeof buf, "CUDA error = %u at %s:%d '%s' (%s)", (unsigned)e_, __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); g_lastError = buf; pt_destroy(c); return PT_E_CUDA; } } while (0)
 	CKC(cudaSetDevice(device));
-	cudaDeviceProp prop;
-	CKC(cudaGetDeviceProperties(&prop, device));
-	c->launch.smCount = prop.multiProcessorCount;
-	c->launch.maxSmemOptin = prop.sharedMemPerBlockOptin;
+	// (two attributes, not cudaGetDeviceProperties: that call fills in everything the driver knows about the device and is one of
+	// the slower ones of a process's start)
+	int smCount = 0, smemOptin = 0;
+	CKC(cudaDeviceGetAttribute(&smCount, cudaDevAttrMultiProcessorCount, device));
+	CKC(cudaDeviceGetAttribute(&smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+	c->launch.smCount = smCount;
+	c->launch.maxSmemOptin = size_t(smemOptin);
 	CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CKC(cudaEventCreate(&c->evStart));
 	CKC(cudaEventCreate(&c->evStop));
