@@ -677,9 +677,20 @@ bool compileScene(size_t count, const pt_object_desc *objects, uint32_t maxLeaf,
 	uint32_t depth = 0;
 	int32_t root;
 	// the builder: SAH unless asked otherwise; kBuilderAuto picks the LBVH for very large scenes, where the build is most of the load
-	const bool lbvh = builder == kBuilderLbvh || (builder == kBuilderAuto && count >= kLbvhAutoCount);
-	if (lbvh) root = buildLbvh(b, nGlobal, count, rootBox, depth);
-	else
+	bool lbvh = builder == kBuilderLbvh || (builder == kBuilderAuto && count >= kLbvhAutoCount);
+	if (lbvh)
+	{
+		root = buildLbvh(b, nGlobal, count, rootBox, depth);
+		// a radix tree is as deep as the keys make it (up to 63 + 32 levels for centroids that crowd towards one point): one that the
+		// traversal stack cannot hold is thrown away and the SAH builder, whose depth is bounded by its median fall-back, takes over
+		if (depth + 2 > uint32_t(kStackSize))
+		{
+			lbvh = false;
+			b.nextNode = 0;
+			b.leafCount = 0;
+		}
+	}
+	if (!lbvh)
 	{
 #pragma omp parallel if (count > 8192)
 #pragma omp single

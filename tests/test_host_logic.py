@@ -285,6 +285,11 @@ def test_bvh_structure():
     _validate_bvh([pt.make_object("SPHERE"), pt.make_object("CUBE", position=(3, 0, 0))], max_leaf=1, builder=1)
     _validate_bvh([pt.make_object("CUBE")] * 9, max_leaf=1, builder=1)
     _validate_bvh([pt.make_object("QUAD", position=(i, 0, 0)) for i in range(5)], max_leaf=1, builder=1)
+    # centroids that crowd towards a point along every axis (one-hot Morton keys): the radix tree is a chain deeper than the
+    # traversal stack - it is thrown away and the SAH builder takes over
+    crowd = [pt.make_object("SPHERE", position=tuple(2.0 ** -k if a == ax else 0.0 for a in range(3)), scale=(1e-9,) * 3) for k in range(21) for ax in range(3)]
+    crowd.append(pt.make_object("SPHERE", scale=(1e-9,) * 3))
+    assert _validate_bvh(crowd, max_leaf=1, builder=1) == _validate_bvh(crowd, max_leaf=1, builder=0)
 
 
 def test_cli_arguments():
